@@ -1,0 +1,264 @@
+/*
+ * tomo_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C, float64 restatement of the native loops of pandekan/tomography_alignment's
+ * projection hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the shipped CUDA path never does.
+ *
+ * PARITY PINNING: the reference ships no tests, golden vectors or fixtures and
+ * its Fortran cannot be compiled in this image (no gfortran).  The oracle is
+ * therefore pinned against (a) the reference's own pure-numpy twins of these loops
+ * (utilities/ray_voxel_utilities.py:173-345), imported from /root/reference with the f2py
+ * modules stubbed -- see tests/golden/make_golden.py and tests/golden/*.npz -- and (b) the
+ * known-answer identities of SURVEY.md section 4.  Everything here follows the cited lines.
+ *
+ * Conventions (all from the reference):
+ *   volume linear index  (x*ny + y)*nz + z            src/ray_wt_grad.f90:38
+ *   ray index            ix*ndz + iz                  utilities/geometry.py:90-94
+ *   sample j of ray r    p = p0[:,r] + (j*step)*rhat[:,r]   utilities/ray_voxel_utilities.py:89-94
+ *   corner order         fff ffc fcf fcc cff cfc ccf ccc (x,y,z)   src/ray_wt_grad.f90:35-89
+ *   every corner is bounds-checked on its own (zero-padded volume)
+ *
+ * Array arguments named p0 / rhat are (3, n_rays) C-order float64, exactly the numpy arrays
+ * the reference builds before it crosses the f2py boundary.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* One sample: floor, floor weights (w_floor = 1 - (p - floor)), as in
+ * utilities/ray_voxel_utilities.py:96-99, then the Fortran's own ceil weights
+ * wt_c = 1 - wt_f (src/ray_wt_grad.f90:29-34). */
+typedef struct {
+    long fx, fy, fz;          /* 0-based floor indices */
+    double wfx, wfy, wfz;     /* floor weights */
+    double wcx, wcy, wcz;     /* ceil weights */
+} sample_t;
+
+static inline void make_sample(const double *p0, const double *rhat, long n_rays, long r,
+                               long j, double step_size, sample_t *s)
+{
+    const double js = (double)j * step_size;      /* j * step_size * r_hat: left to right */
+    const double px = p0[0 * n_rays + r] + js * rhat[0 * n_rays + r];
+    const double py = p0[1 * n_rays + r] + js * rhat[1 * n_rays + r];
+    const double pz = p0[2 * n_rays + r] + js * rhat[2 * n_rays + r];
+    const double flx = floor(px), fly = floor(py), flz = floor(pz);
+    s->fx = (long)flx; s->fy = (long)fly; s->fz = (long)flz;
+    s->wfx = 1.0 - (px - flx); s->wfy = 1.0 - (py - fly); s->wfz = 1.0 - (pz - flz);
+    s->wcx = 1.0 - s->wfx; s->wcy = 1.0 - s->wfy; s->wcz = 1.0 - s->wfz;
+}
+
+#define IN(i, n) ((i) >= 0 && (i) < (n))
+
+/* Number of threads the library will use (1 without OpenMP). */
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* COO emitter: restates trilinear_ray_sparse, src/ray_wt_grad.f90:1-92.
+ * dat/det/wts must hold 8*n_rays*n entries; returns the number written (n_inds).
+ * Unused tail is set to -999 like the Fortran (ray_wt_grad.f90:15-17). */
+long orc_ray_sparse(const double *p0, const double *rhat, long n_rays, long n, double step_size,
+                    long nx, long ny, long nz, int32_t *dat, int32_t *det, double *wts)
+{
+    const long cap = 8 * n_rays * n;
+    for (long i = 0; i < cap; ++i) { dat[i] = -999; det[i] = -999; wts[i] = -999.0; }
+    long k = 0;
+    for (long r = 0; r < n_rays; ++r) {
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) {
+                if (IN(X[a], nx) && IN(Y[b], ny) && IN(Z[c], nz)) {
+                    det[k] = (int32_t)r;
+                    dat[k] = (int32_t)((X[a] * ny + Y[b]) * nz + Z[c]);
+                    wts[k] = WX[a] * WY[b] * WZ[c];
+                    ++k;
+                }
+            }
+        }
+    }
+    return k;
+}
+
+/* y[r] = sum_j sum_corners w * vol[corner]  ==  row r of A applied to vol, float64 accumulate.
+ * A is the matrix trilinear_ray_sparse emits (src/ray_wt_grad.f90:20-91) once duplicates are
+ * summed (utilities/projection_operators.py:72-76).  If w32 != 0 every weight is first rounded
+ * to float32 the way projection_operators.py:106 does (wts.astype(precision)). */
+void orc_forward_view(const double *p0, const double *rhat, long n_rays, long n, double step_size,
+                      long nx, long ny, long nz, const double *vol, int w32, double *proj)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < n_rays; ++r) {
+        double acc = 0.0;
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            for (int a = 0; a < 2; ++a) { if (!IN(X[a], nx)) continue;
+                for (int b = 0; b < 2; ++b) { if (!IN(Y[b], ny)) continue;
+                    for (int c = 0; c < 2; ++c) { if (!IN(Z[c], nz)) continue;
+                        double w = WX[a] * WY[b] * WZ[c];
+                        if (w32) w = (double)(float)w;
+                        acc += w * vol[(X[a] * ny + Y[b]) * nz + Z[c]];
+                    } } }
+        }
+        proj[r] = acc;
+    }
+}
+
+/* vol += A^T y for one view: the exact transpose of orc_forward_view (the backprojection every
+ * solver of the reference uses: recon/sirt.py:61, recon/cgls.py:54,72).  Serial scatter, float64. */
+void orc_adjoint_view(const double *p0, const double *rhat, long n_rays, long n, double step_size,
+                      long nx, long ny, long nz, const double *y, int w32, double *vol)
+{
+    for (long r = 0; r < n_rays; ++r) {
+        const double yr = y[r];
+        if (yr == 0.0) continue;
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            for (int a = 0; a < 2; ++a) { if (!IN(X[a], nx)) continue;
+                for (int b = 0; b < 2; ++b) { if (!IN(Y[b], ny)) continue;
+                    for (int c = 0; c < 2; ++c) { if (!IN(Z[c], nz)) continue;
+                        double w = WX[a] * WY[b] * WZ[c];
+                        if (w32) w = (double)(float)w;
+                        vol[(X[a] * ny + Y[b]) * nz + Z[c]] += w * yr;
+                    } } }
+        }
+    }
+}
+
+/* Projection + gradient image for one view: restates trilinear_ray_interp,
+ * src/ray_wt_grad.f90:95-223.
+ *   der   (9, 3, n_rays) C-order, from derivative_ray_points (ray_voxel_utilities.py:15-50)
+ *   step(r, j) = j*step_size/r_length0           (ray_voxel_utilities.py:148-151)
+ *   g(0:3,:) = der(0:3,:,r);  g(3+k,:) = der(3+k,:,r) + step*der(6+k,:,r)   (ray_wt_grad.f90:136-141)
+ *   per in-bounds corner: det_img += rec*w;  grad += rec*(sx*wy*wz*g[:,0] + sy*wx*wz*g[:,1] + sz*wx*wy*g[:,2])
+ *   with s = -1 for a floor index and +1 for a ceil index on that axis (ray_wt_grad.f90:142-220).
+ * det_img (n_rays), grad (6, n_rays) C-order == the Fortran's (6, n_rays) array as numpy sees it. */
+void orc_interp_grad_view(const double *p0, const double *rhat, long n_rays, long n,
+                          double step_size, double r_length0, long nx, long ny, long nz,
+                          const double *vol, const double *der, double *det_img, double *grad)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < n_rays; ++r) {
+        double acc = 0.0, ga[6] = {0, 0, 0, 0, 0, 0};
+        double d[9][3];
+        for (int k = 0; k < 9; ++k) for (int a = 0; a < 3; ++a)
+            d[k][a] = der[((long)k * 3 + a) * n_rays + r];
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const double st = (double)j * step_size / r_length0;
+            double g[6][3];
+            for (int a = 0; a < 3; ++a) {
+                g[0][a] = d[0][a]; g[1][a] = d[1][a]; g[2][a] = d[2][a];
+                g[3][a] = d[3][a] + st * d[6][a];
+                g[4][a] = d[4][a] + st * d[7][a];
+                g[5][a] = d[5][a] + st * d[8][a];
+            }
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            const double SG[2] = {-1.0, 1.0};
+            for (int a = 0; a < 2; ++a) { if (!IN(X[a], nx)) continue;
+                for (int b = 0; b < 2; ++b) { if (!IN(Y[b], ny)) continue;
+                    for (int c = 0; c < 2; ++c) { if (!IN(Z[c], nz)) continue;
+                        const double v = vol[(X[a] * ny + Y[b]) * nz + Z[c]];
+                        acc += v * (WX[a] * WY[b] * WZ[c]);
+                        const double c1 = SG[a] * WY[b] * WZ[c] * v;
+                        const double c2 = SG[b] * WX[a] * WZ[c] * v;
+                        const double c3 = SG[c] * WX[a] * WY[b] * v;
+                        for (int k = 0; k < 6; ++k)
+                            ga[k] += c1 * g[k][0] + c2 * g[k][1] + c3 * g[k][2];
+                    } } }
+        }
+        det_img[r] = acc;
+        for (int k = 0; k < 6; ++k) grad[(long)k * n_rays + r] = ga[k];
+    }
+}
+
+/* ---- orphan (matrix-free, never called from Python) voxel-driven semantics ----------------- */
+
+/* vox += bilinear gather of one view's detector image at the rotated voxel centres.
+ * Restates voxel_rigid_transformation + voxel_back_bilinear,
+ * src/external_back_projection.f90:1-68, called per view by back_project,
+ * src/back_projection.f90:25-32.  rot is the row-major 3x3 matrix Ry(b)*Rx(a)*Rz(p) and tr the
+ * vector Ry(b)*t, so that x' = rot*x + tr == Ry(b)*(Rx(a)*Rz(p)*x + t)  (f90:17-25).
+ * centres (3, n_vox) C-order, det_image (ndx, ndz) C-order (the Fortran's det_image(np,:,:)).
+ * Four taps, each bounds-checked on its own; the y coordinate is ignored (f90:47-66). */
+void orc_voxel_back_view(const double *rot, const double *tr, const double *centres, long n_vox,
+                         const double *origin, const double *det_image, long ndx, long ndz,
+                         double *vox)
+{
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n_vox; ++i) {
+        const double x = centres[i], y = centres[n_vox + i], z = centres[2 * n_vox + i];
+        const double xr = rot[0] * x + rot[1] * y + rot[2] * z + tr[0];
+        const double zr = rot[6] * x + rot[7] * y + rot[8] * z + tr[2];
+        const double ux = xr - origin[0], uz = zr - origin[2];
+        const double flx = floor(ux), flz = floor(uz);
+        const long fx = (long)flx, fz = (long)flz;
+        const double ax = ux - flx, az = uz - flz;
+        double acc = 0.0;
+        if (IN(fx, ndx) && IN(fz, ndz))         acc += det_image[fx * ndz + fz] * (1.0 - ax) * (1.0 - az);
+        if (IN(fx + 1, ndx) && IN(fz, ndz))     acc += det_image[(fx + 1) * ndz + fz] * ax * (1.0 - az);
+        if (IN(fx, ndx) && IN(fz + 1, ndz))     acc += det_image[fx * ndz + fz + 1] * (1.0 - ax) * az;
+        if (IN(fx + 1, ndx) && IN(fz + 1, ndz)) acc += det_image[(fx + 1) * ndz + fz + 1] * ax * az;
+        vox[i] += acc;
+    }
+}
+
+/* Voxel-driven forward splat + gradient image: restates bilinear_vox_interp,
+ * src/vox_wt_grad.f90:1-55.  floor_x/floor_z/alpha_x/alpha_z/rec are (n_vox); der is
+ * (6, 3, n_vox) C-order (numpy view of the Fortran der_points(:,:,i)); outputs use the
+ * Fortran's detector layout det_img(fz, fx) flattened with x FASTEST, i.e. index fz + ndz*fx in
+ * Fortran order == numpy det_img.ravel() of the (ndz, ndx) array returned by f2py, index
+ * fz*ndx + fx.  grad is (6, ndz, ndx) C-order. */
+void orc_voxel_splat_grad(long n_vox, const int32_t *floor_x, const int32_t *floor_z,
+                          const double *alpha_x, const double *alpha_z, const double *rec,
+                          long ndx, long ndz, const double *der, double *det_img, double *grad)
+{
+    memset(det_img, 0, sizeof(double) * (size_t)(ndx * ndz));
+    memset(grad, 0, sizeof(double) * (size_t)(6 * ndx * ndz));
+    for (long i = 0; i < n_vox; ++i) {
+        const long fx = floor_x[i], fz = floor_z[i];
+        const double ax = alpha_x[i], az = alpha_z[i], v = rec[i];
+        /* weights and d(weight)/d(alpha) sign pattern, vox_wt_grad.f90:25-50 */
+        const long TX[4] = {fx, fx + 1, fx, fx + 1};
+        const long TZ[4] = {fz, fz, fz + 1, fz + 1};
+        const double W[4]  = {(1.0 - ax) * (1.0 - az), ax * (1.0 - az), (1.0 - ax) * az, ax * az};
+        const double G0[4] = {(1.0 - az), -(1.0 - az), az, -az};      /* factor on g(:,1) */
+        const double G2[4] = {(1.0 - ax), ax, -(1.0 - ax), -ax};      /* factor on g(:,3) */
+        for (int t = 0; t < 4; ++t) {
+            if (!(IN(TX[t], ndx) && IN(TZ[t], ndz))) continue;
+            const long di = TZ[t] * ndx + TX[t];
+            det_img[di] += v * W[t];
+            for (int k = 0; k < 6; ++k) {
+                const double g1 = der[((long)k * 3 + 0) * n_vox + i];
+                const double g3 = der[((long)k * 3 + 2) * n_vox + i];
+                grad[(long)k * ndx * ndz + di] += g1 * G0[t] * v + g3 * G2[t] * v;
+            }
+        }
+    }
+}
