@@ -1,0 +1,132 @@
+/*
+ * tomo_b200.h -- C ABI of libtomo_b200.so: B200 (sm_100a) projection operators for
+ * pandekan/tomography_alignment.
+ *
+ * The reference has no C ABI; its native boundary is f2py around Fortran 90.  Each entry point
+ * below names the reference interface it replaces (file:line under the reference tree).  All
+ * pointers suffixed _dev are raw CUDA device pointers owned by the caller (e.g. torch
+ * tensor.data_ptr()); the library allocates no device memory.  `stream` is a cudaStream_t passed
+ * as void* (NULL = legacy default stream).  Calls are asynchronous with respect to the host unless
+ * stated, re-entrant, and keep no global state except the thread-local last-error string.
+ *
+ * Return value: 0 on success, a negative TOMO_E_* code for argument errors, a positive
+ * cudaError_t value for CUDA failures.  Nothing throws across the ABI.
+ *
+ * Layouts (all from the reference):
+ *   volume        float32 [nx][ny][nz], z fastest              src/ray_wt_grad.f90:38
+ *   projections   float32 [n_proj][ndx][ndz], iz fastest       utilities/geometry.py:90-94,
+ *                                                              utilities/projection_operators.py:108
+ *   poses         float64 [n_proj][9] = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z
+ *                 (angles, xyz_shift and Geometry.cor_shift rows of projection_operators.py:50-52,97-102;
+ *                 only cor_x is used, ray_voxel_utilities.py:72-73)
+ *   gradients     order [tx, ty, tz, phi, alpha, beta]         utilities/ray_voxel_utilities.py:39-46
+ */
+#ifndef TOMO_B200_H
+#define TOMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOMO_B200_VERSION 100            /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define TOMO_API __attribute__((visibility("default")))
+#else
+#define TOMO_API
+#endif
+
+#define TOMO_E_ARG        (-1)           /* NULL pointer / non-positive size */
+#define TOMO_E_GEOM       (-2)           /* geometry not representable (e.g. zero step) */
+#define TOMO_E_WORKSPACE  (-3)           /* workspace too small */
+#define TOMO_E_RANGE      (-4)           /* size exceeds 32-bit index budget of the kernels */
+
+/* Doubles per view in the device-side view table written by tomo_views_*. */
+#define TOMO_VIEW_STRIDE  96
+#define TOMO_POSE_STRIDE  9
+/* Zero border (voxels) of the padded volume on every side of every axis. */
+#define TOMO_PAD          2
+
+/* Parallel-beam geometry: the scalars utilities/geometry.py:14-105 derives its grids from. */
+typedef struct TomoGeom {
+    int32_t nx, ny, nz;        /* Geometry.vox_shape */
+    int32_t ndx, ndz;          /* Geometry.det_shape */
+    double  vox_origin[3];     /* Geometry.vox_origin = first voxel centre (geometry.py:87) */
+    double  vox_pix[3];        /* Geometry.vox_pix (centre spacing, geometry.py:82-84) */
+    double  det_x0, det_z0;    /* first detector-pixel centre (geometry.py:92-93) */
+    double  det_dx, det_dz;    /* detector pitch */
+    double  src_y, det_y;      /* source / detector plane y = -sy / +sy (geometry.py:95-100) */
+    double  step_size;         /* Geometry.step_size */
+} TomoGeom;
+
+TOMO_API int         tomo_version(void);
+TOMO_API const char* tomo_last_error(void);
+
+/* ---- per-view constants --------------------------------------------------------------------- */
+/* Host-only, float64: the per-view setup of forward_sparse / forward_proj_grad
+ * (utilities/ray_voxel_utilities.py:66-94,124-159) and derivative_ray_points (:15-50) reduced to
+ * the affine lattice  p(ix,iz,j) = P00 + ix*U + iz*W + j*D  and the affine pose-derivative tables.
+ * out_host: [n_proj][TOMO_VIEW_STRIDE] doubles.  No CUDA call is made. */
+TOMO_API int tomo_views_compute_host(const TomoGeom* geom, const double* poses, int n_proj, double* out_host);
+TOMO_API size_t tomo_views_bytes(int n_proj);
+/* Same, then cudaMemcpyAsync into views_dev (tomo_views_bytes(n_proj) bytes) on `stream`; the host
+ * staging copy is synchronised before return so `poses` may be reused immediately. */
+TOMO_API int tomo_views_upload(const TomoGeom* geom, const double* poses, int n_proj, void* views_dev, void* stream);
+
+/* ---- padded volume -------------------------------------------------------------------------- */
+/* The ray-driven kernels read a zero-bordered copy of the volume (zero-padded-corner semantics of
+ * src/ray_wt_grad.f90:35-89 without per-corner branches): [nx+2P][ny+2P][nzp], nzp = nz+2P rounded
+ * up to 32 floats, data at offset (P,P,P), P = TOMO_PAD. */
+TOMO_API size_t tomo_padded_volume_bytes(const TomoGeom* geom);
+TOMO_API int tomo_pad_volume(const TomoGeom* geom, const float* vol_dev, float* volpad_dev, void* stream);
+
+/* ---- operators ------------------------------------------------------------------------------ */
+/* proj = A x for all views.  Replaces building A with trilinear_ray_sparse
+ * (src/ray_wt_grad.f90:1-92 via utilities/projection_operators.py:54-76,95-110) and
+ * sparse.csr_matrix.dot(A, x) (recon/sirt.py:59); also forward_project
+ * (src/forward_projection.f90:1-68). */
+TOMO_API int tomo_forward(const TomoGeom* geom, const void* views_dev, int n_proj,
+                 const float* volpad_dev, float* proj_dev, void* stream);
+
+/* vol (+)= A^T y, the exact transpose of tomo_forward: replaces
+ * sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A), y) (recon/sirt.py:61, recon/cgls.py:54,72).
+ * Gather formulation, no atomics, bitwise deterministic.  vol_dev is the UNPADDED volume. */
+TOMO_API int tomo_back_adjoint(const TomoGeom* geom, const void* views_dev, int n_proj,
+                      const float* proj_dev, float* vol_dev, int accumulate, void* stream);
+
+/* vol (+)= voxel-driven bilinear backprojection, the orphan matrix-free back_project
+ * (src/back_projection.f90:1-34, src/external_back_projection.f90:1-68): x' = Ry(b)(Rx(a)Rz(p)x + t),
+ * 4 bilinear taps of the view's image at (x'_x - origin_x, x'_z - origin_z), y ignored.
+ * NOT the transpose of tomo_forward (inverse pose convention).  origin[3] is the
+ * Fortran's `origin` argument; det images use the [n_proj][ndx][ndz] layout above. */
+TOMO_API int tomo_back_voxel_bilinear(const TomoGeom* geom, const void* views_dev, int n_proj,
+                             const double origin[3], const float* proj_dev, float* vol_dev,
+                             int accumulate, void* stream);
+
+/* Projection + 6-DOF rigid-body gradient for all views in one launch.  Replaces
+ * ProjectionMatrix.projection_gradient (utilities/projection_operators.py:112-122) ->
+ * forward_proj_grad (utilities/ray_voxel_utilities.py:113-170) -> trilinear_ray_interp
+ * (src/ray_wt_grad.f90:95-223), and compute_gradient (src/projection_gradient.f90:1-79).
+ *   proj_dev   [n_proj][n_det]      float32, nullable
+ *   dproj_dev  [n_proj][6][n_det]   float32, nullable: d proj / d theta per ray (the `grad` the
+ *              reference returns)
+ *   meas_dev   [n_proj][n_det]      float32, nullable: measured projections b
+ *   grad6_dev  [n_proj][6]          float64, nullable (needs meas): sum_rays (-dproj_k)*(b - proj),
+ *              i.e. np.dot(s, residual) of utilities/alignment_functions.py:27-37,176-186
+ *   cost_dev   [n_proj]             float64, nullable (needs meas): 0.5*||b - proj||^2
+ *              (utilities/alignment_functions.py:163)
+ * grad6/cost are reduced in float64 in a fixed order (bitwise deterministic); they need
+ * tomo_proj_grad_workspace_bytes() bytes of workspace. */
+TOMO_API size_t tomo_proj_grad_workspace_bytes(const TomoGeom* geom, int n_proj);
+TOMO_API int tomo_proj_grad(const TomoGeom* geom, const void* views_dev, int n_proj,
+                   const float* volpad_dev, const float* meas_dev,
+                   float* proj_dev, float* dproj_dev, double* grad6_dev, double* cost_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOMO_B200_H */

@@ -1,0 +1,74 @@
+// emu.cpp -- TEST HARNESS ONLY: runs the __host__ __device__ cores of the CUDA kernels
+// (tomography_alignment_b200/csrc/ray_core.h, back_core.h) on the CPU, one loop iteration per
+// GPU thread, so the kernel arithmetic can be checked against the oracle in the CPU-only test tier.
+// The product never loads this library.
+#include <cstddef>
+#include <vector>
+#include "../../tomography_alignment_b200/csrc/ray_core.h"
+#include "../../tomography_alignment_b200/csrc/back_core.h"
+
+#define EMU_API extern "C" __attribute__((visibility("default")))
+
+EMU_API void emu_pad(const TomoGeom* g, const float* vol, float* pad)
+{
+    const int nyp = g->ny + 2 * TOMO_PAD, nzp = tomo_nzp(g->nz), nxp = g->nx + 2 * TOMO_PAD;
+    for (size_t i = 0; i < (size_t)nxp * nyp * nzp; ++i) pad[i] = 0.f;
+    for (int x = 0; x < g->nx; ++x) for (int y = 0; y < g->ny; ++y) for (int z = 0; z < g->nz; ++z)
+        pad[((size_t)(x + TOMO_PAD) * nyp + y + TOMO_PAD) * nzp + z + TOMO_PAD] = vol[((size_t)x * g->ny + y) * g->nz + z];
+}
+
+EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, const float* volpad,
+                           const float* meas, float* proj, float* dproj, double* grad6, double* cost, int want_grad)
+{
+    const RayDims dm = {g->nx, g->ny, g->nz, (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz), tomo_nzp(g->nz)};
+    const size_t n_det = (size_t)g->ndx * g->ndz;
+    for (int v = 0; v < n_proj; ++v) {
+        const double* V = views + (size_t)v * TOMO_VIEW_STRIDE;
+        double red[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int ix = 0; ix < g->ndx; ++ix) {
+            double loc[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int iz = 0; iz < g->ndz; ++iz) {
+                const size_t ray = (size_t)ix * g->ndz + iz;
+                RaySums s;
+                if (want_grad) ray_march<true>(volpad, V, dm, ix, iz, s); else ray_march<false>(volpad, V, dm, ix, iz, s);
+                if (proj) proj[v * n_det + ray] = s.acc;
+                if (want_grad) {
+                    float dp[6];
+                    ray_gradient(V, ix, iz, s, dp);
+                    if (dproj) for (int k = 0; k < 6; ++k) dproj[((size_t)v * 6 + k) * n_det + ray] = dp[k];
+                    if (meas) {
+                        const double res = (double)meas[v * n_det + ray] - (double)s.acc;
+                        for (int k = 0; k < 6; ++k) loc[k] += -(double)dp[k] * res;
+                        loc[6] += 0.5 * res * res;
+                    }
+                }
+            }
+#pragma omp critical
+            for (int k = 0; k < 7; ++k) red[k] += loc[k];
+        }
+        if (grad6) for (int k = 0; k < 6; ++k) grad6[v * 6 + k] = red[k];
+        if (cost) cost[v] = red[6];
+    }
+}
+
+EMU_API void emu_back(const TomoGeom* g, const double* views, int n_proj, const float* proj, float* vol,
+                      int accumulate, int voxel_bilinear, const double* origin)
+{
+    const size_t n_det = (size_t)g->ndx * g->ndz;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int x = 0; x < g->nx; ++x) for (int y = 0; y < g->ny; ++y) for (int z = 0; z < g->nz; ++z) {
+        float acc = 0.f;
+        for (int v = 0; v < n_proj; ++v) {
+            const double* V = views + (size_t)v * TOMO_VIEW_STRIDE;
+            if (voxel_bilinear)
+                acc += voxel_bilinear_view(proj + v * n_det, V, g->ndx, g->ndz, origin,
+                                           g->vox_origin[0] + x * g->vox_pix[0], g->vox_origin[1] + y * g->vox_pix[1],
+                                           g->vox_origin[2] + z * g->vox_pix[2]);
+            else
+                acc += adjoint_gather_view(proj + v * n_det, V, g->ndx, g->ndz, x, y, z);
+        }
+        const size_t vi = ((size_t)x * g->ny + y) * g->nz + z;
+        vol[vi] = accumulate ? vol[vi] + acc : acc;
+    }
+}

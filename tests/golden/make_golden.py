@@ -107,6 +107,13 @@ def main():
     out["rot/angles"] = angs
     for fn in ("rot_x", "rot_y", "rot_z", "der_rot_x", "der_rot_y", "der_rot_z"):
         out["rot/" + fn] = np.array([getattr(rotations, fn)(a) for a in angs])
+    # the reference's Shepp-Logan generator; np.lib.index_tricks was made private in numpy 2
+    # (SURVEY.md F8), so alias it for the import -- the reference's file is untouched
+    if not hasattr(np.lib, "index_tricks"):
+        np.lib.index_tricks = np.lib._index_tricks_impl
+    from utilities import generate_phantom
+    for n in (16, 24):
+        out["shepp3d/%d" % n] = generate_phantom.shepp3d(n)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -1,0 +1,118 @@
+"""The __host__ __device__ cores of the CUDA kernels (csrc/ray_core.h, back_core.h), executed on the CPU by
+tests/emu, against the oracle.  Tolerances are BASELINE.json's: relative L2 <= 1e-5 for projections and
+backprojections, <= 1e-4 for the alignment gradients."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tomography_alignment_b200 import pose_table
+from helpers import EmuBackend, make_geoms, random_poses, rel_l2
+
+TOL_PROJ, TOL_GRAD = 1e-5, 1e-4
+
+CASES = [
+    # shape, dshape, n_proj, kwargs
+    ((16, 16, 16), (16, 16), 6, dict()),
+    ((24, 20, 18), (24, 18), 5, dict(cor=[0.7, 0, 0])),
+    ((16, 16, 16), (20, 12), 5, dict(tilt=0.2, shift=5.0)),            # detector != volume, big jitter
+    ((16, 16, 16), (16, 16), 4, dict(step=0.5)),
+    ((16, 16, 16), (16, 16), 4, dict(step=1.7)),                       # |D| > 1: integer part in the address step
+    ((12, 12, 12), (12, 12), 3, dict(shift=14.0, phis=[0.2, 1.1, 2.0])),   # rays mostly / entirely miss the volume
+    ((5, 40, 3), (5, 3), 3, dict()),                                   # ragged: tiny x/z, long y
+    ((33, 9, 35), (33, 35), 2, dict(phis=[0.4, 2.9])),                 # not a multiple of the 32x8 tile
+]
+
+
+def setup(shape, dshape, n_proj, cor=None, step=1.0, tilt=0.02, shift=2.0, phis=None, seed=0):
+    g, og = make_geoms(shape, dshape, n_proj, cor=cor, step=step)
+    phi, alpha, beta, xyz = random_poses(n_proj, seed, tilt=tilt, shift=shift, phis=phis)
+    be = EmuBackend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    return g, og, be, op, (phi, alpha, beta, xyz)
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES)
+def test_forward_and_adjoint(shape, dshape, n_proj, kw):
+    g, og, be, op, _ = setup(shape, dshape, n_proj, **kw)
+    rng = np.random.default_rng(1)
+    vol = rng.random(shape).astype(np.float32)
+    ref = op.forward(vol)
+    got = be.forward(vol).numpy().reshape(n_proj, -1)
+    if np.linalg.norm(ref) > 0:
+        assert rel_l2(got, ref) <= TOL_PROJ
+    else:
+        assert np.abs(got).max() == 0.0
+    y = rng.random((n_proj, og.n_det)).astype(np.float32)
+    refb = op.adjoint(y)
+    gotb = be.adjoint(y).numpy().ravel()
+    if np.linalg.norm(refb) > 0:
+        assert rel_l2(gotb, refb) <= TOL_PROJ
+    else:
+        assert np.abs(gotb).max() == 0.0
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES[:5])
+def test_projection_gradient(shape, dshape, n_proj, kw):
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)
+    rng = np.random.default_rng(2)
+    vol = rng.random(shape).astype(np.float32)
+    meas = (op.forward(vol) * 1.02 + 0.05).astype(np.float32)
+    out = be.proj_grad(vol, meas=meas)
+    for i in range(n_proj):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["proj"][i].numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][i].numpy(), gr) <= TOL_GRAD
+        res = meas[i].astype(np.float64) - p
+        assert rel_l2(out["grad6"][i].numpy(), -gr @ res) <= TOL_GRAD
+        assert abs(out["cost"][i].item() - 0.5 * res @ res) <= 1e-5 * (0.5 * res @ res)
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES[:3])
+def test_voxel_driven_bilinear_backprojector(shape, dshape, n_proj, kw):
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)
+    y = np.random.default_rng(3).random((n_proj,) + tuple(dshape)).astype(np.float32)
+    ref = O.voxel_back_project(og, y, alpha, beta, phi, xyz)
+    assert rel_l2(be.voxel_back(y).numpy(), ref) <= TOL_PROJ
+
+
+def test_exact_lattice_pose_phi0():
+    """phi = alpha = beta = 0, t = 0: every sample sits on a lattice plane in x and z.  Projection = sum over y,
+    and the one-sided derivatives agree with the reference because the floor of an exact integer is exact."""
+    g, og, be, op, _ = setup((12, 10, 9), (12, 9), 1, tilt=0.0, shift=0.0, phis=[0.0])
+    vol = np.random.default_rng(4).random((12, 10, 9)).astype(np.float32)
+    out = be.proj_grad(vol)
+    np.testing.assert_allclose(out["proj"][0].numpy(), vol.astype(np.float64).sum(axis=1), rtol=2e-6)
+    p, gr = O.forward_proj_grad(og, 0.0, 0.0, 0.0, np.zeros(3), np.zeros(3), vol)
+    for k in (0, 2, 3, 4, 5):      # row 1 (ty) is identically ~0
+        assert rel_l2(out["dproj"][0, k].numpy(), gr[k]) <= TOL_GRAD
+
+
+def test_against_reference_numpy_golden():
+    """Directly against the reference-authored fixtures (zero-shell volumes, see make_golden.py)."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_numpy_cases.npz"))
+    for name in gold["case_names"]:
+        q = lambda k: gold["%s/%s" % (name, k)]
+        alpha, beta, phi = (float(v) for v in q("pose"))
+        g, _ = make_geoms(tuple(q("vox_shape")), tuple(q("det_shape")), 1, cor=q("cor"), step=float(q("step")))
+        be = EmuBackend(g)
+        be.set_poses(pose_table(np.array([[phi, alpha, beta]]), q("xyz")[None, :], q("cor")[None, :]))
+        out = be.proj_grad(q("rec").astype(np.float32))
+        assert rel_l2(out["proj"][0].numpy(), q("proj")) <= TOL_PROJ, name
+        assert rel_l2(out["dproj"][0].numpy(), q("grad")) <= TOL_GRAD, name
+        shape = tuple(q("vox_shape"))
+        at = be.adjoint(q("y")[None, :].astype(np.float32)).numpy().reshape(shape)[1:-1, 1:-1, 1:-1]
+        assert rel_l2(at, q("At_dot_y").reshape(shape)[1:-1, 1:-1, 1:-1]) <= TOL_PROJ, name
+
+
+def test_adjoint_pair_at_64cubed():
+    """<A x, y> = <x, A^T y> for the emulated kernel pair at the reference's example size (64^3, 4 views)."""
+    g, og, be, op, _ = setup((64, 64, 64), (64, 64), 4, seed=9, phis=[0.1, 0.9, 1.7, 2.8])
+    rng = np.random.default_rng(10)
+    x = rng.random((64, 64, 64)).astype(np.float32)
+    y = rng.random((4, 64 * 64)).astype(np.float32)
+    lhs = np.vdot(be.forward(x).numpy().astype(np.float64).ravel(), y.astype(np.float64).ravel())
+    rhs = np.vdot(x.astype(np.float64).ravel(), be.adjoint(y).numpy().astype(np.float64).ravel())
+    assert abs(lhs - rhs) <= 1e-6 * abs(rhs)

@@ -1,0 +1,238 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libtomo_b200.so), against the
+CPU oracle on the same seeded inputs.  Tolerances are BASELINE.json's: relative L2 <= 1e-5 for projections
+and backprojections, <= 1e-4 for the alignment gradients."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy import sparse
+
+from oracle import oracle as O
+from tomography_alignment_b200 import Geometry, ProjectionMatrix, pose_table
+from tomography_alignment_b200.phantom import benchmark_poses, shepp3d
+from helpers import EmuBackend, make_geoms, random_poses, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_PROJ, TOL_GRAD = 1e-5, 1e-4
+
+CASES = [
+    ((16, 16, 16), (16, 16), 6, dict()),
+    ((24, 20, 18), (24, 18), 5, dict(cor=[0.7, 0, 0])),
+    ((16, 16, 16), (20, 12), 5, dict(tilt=0.2, shift=5.0)),
+    ((16, 16, 16), (16, 16), 4, dict(step=0.5)),
+    ((16, 16, 16), (16, 16), 4, dict(step=1.7)),
+    ((12, 12, 12), (12, 12), 3, dict(shift=14.0, phis=[0.2, 1.1, 2.0])),
+    ((5, 40, 3), (5, 3), 3, dict()),
+    ((33, 9, 35), (33, 35), 2, dict(phis=[0.4, 2.9])),
+    ((40, 40, 40), (40, 40), 1, dict(phis=[0.77])),                       # n_proj == 1
+]
+
+
+def cuda_backend(g):
+    from tomography_alignment_b200.cuda_backend import CudaBackend
+    return CudaBackend(g, "cuda:0")
+
+
+def setup(shape, dshape, n_proj, cor=None, step=1.0, tilt=0.02, shift=2.0, phis=None, seed=0):
+    g, og = make_geoms(shape, dshape, n_proj, cor=cor, step=step)
+    phi, alpha, beta, xyz = random_poses(n_proj, seed, tilt=tilt, shift=shift, phis=phis)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    return g, og, be, op, (phi, alpha, beta, xyz)
+
+
+def test_native_library_is_loaded():
+    import ctypes
+    from tomography_alignment_b200 import _lib
+    L = _lib.load()
+    assert isinstance(L, ctypes.CDLL) and L.tomo_version() >= 100
+    maps = open("/proc/self/maps").read()
+    assert "libtomo_b200.so" in maps
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES)
+def test_forward_and_adjoint_vs_oracle(shape, dshape, n_proj, kw):
+    g, og, be, op, _ = setup(shape, dshape, n_proj, **kw)
+    rng = np.random.default_rng(1)
+    vol = rng.random(shape).astype(np.float32)
+    ref = op.forward(vol)
+    got = be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1)
+    if np.linalg.norm(ref) > 0:
+        assert rel_l2(got, ref) <= TOL_PROJ
+    else:
+        assert np.abs(got).max() == 0.0
+    y = rng.random((n_proj, og.n_det)).astype(np.float32)
+    refb = op.adjoint(y)
+    gotb = be.adjoint(torch.as_tensor(y)).cpu().numpy().ravel()
+    if np.linalg.norm(refb) > 0:
+        assert rel_l2(gotb, refb) <= TOL_PROJ
+    else:
+        assert np.abs(gotb).max() == 0.0
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES[:5] + CASES[8:])
+def test_projection_gradient_vs_oracle(shape, dshape, n_proj, kw):
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)
+    rng = np.random.default_rng(2)
+    vol = rng.random(shape).astype(np.float32)
+    meas = (op.forward(vol) * 1.02 + 0.05).astype(np.float32)
+    out = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(meas))
+    for i in range(n_proj):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["proj"][i].cpu().numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][i].cpu().numpy(), gr) <= TOL_GRAD
+        res = meas[i].astype(np.float64) - p
+        assert rel_l2(out["grad6"][i].cpu().numpy(), -gr @ res) <= TOL_GRAD
+        assert abs(out["cost"][i].item() - 0.5 * res @ res) <= 1e-5 * (0.5 * res @ res)
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES[:3])
+def test_voxel_driven_bilinear_backprojector(shape, dshape, n_proj, kw):
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)
+    y = np.random.default_rng(3).random((n_proj,) + tuple(dshape)).astype(np.float32)
+    ref = O.voxel_back_project(og, y, alpha, beta, phi, xyz)
+    assert rel_l2(be.voxel_back(torch.as_tensor(y)).cpu().numpy(), ref) <= TOL_PROJ
+
+
+def test_reference_numpy_golden_fixtures():
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_numpy_cases.npz"))
+    for name in gold["case_names"]:
+        q = lambda k: gold["%s/%s" % (name, k)]
+        alpha, beta, phi = (float(v) for v in q("pose"))
+        g, _ = make_geoms(tuple(q("vox_shape")), tuple(q("det_shape")), 1, cor=q("cor"), step=float(q("step")))
+        be = cuda_backend(g)
+        be.set_poses(pose_table(np.array([[phi, alpha, beta]]), q("xyz")[None, :], q("cor")[None, :]))
+        out = be.proj_grad(torch.as_tensor(q("rec").astype(np.float32)))
+        assert rel_l2(out["proj"][0].cpu().numpy(), q("proj")) <= TOL_PROJ, name
+        assert rel_l2(out["dproj"][0].cpu().numpy(), q("grad")) <= TOL_GRAD, name
+        shape = tuple(q("vox_shape"))
+        at = be.adjoint(torch.as_tensor(q("y")[None, :].astype(np.float32))).cpu().numpy().reshape(shape)
+        assert rel_l2(at[1:-1, 1:-1, 1:-1], q("At_dot_y").reshape(shape)[1:-1, 1:-1, 1:-1]) <= TOL_PROJ, name
+
+
+def test_gpu_equals_cpu_emulation_of_the_same_cores():
+    """The kernels and tests/emu run the same __host__ __device__ code; results agree to rounding."""
+    shape, dshape, n_proj = (20, 24, 28), (20, 28), 4
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, seed=5)
+    emu = EmuBackend(g)
+    emu.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    vol = np.random.default_rng(6).random(shape).astype(np.float32)
+    a = be.proj_grad(torch.as_tensor(vol))
+    b = emu.proj_grad(vol)
+    assert rel_l2(a["proj"].cpu().numpy(), b["proj"].numpy()) < 1e-6
+    assert rel_l2(a["dproj"].cpu().numpy(), b["dproj"].numpy()) < 1e-5
+
+
+def test_config0_64cubed_90_views_shepp_logan():
+    """BASELINE.json configs[0]: 64^3 phantom, 90 views with the jitter of examples/generate_data.py."""
+    n, n_proj = 64, 90
+    g, og = make_geoms((n, n, n), (n, n), n_proj)
+    phi, alpha, beta, xyz = benchmark_poses(n_proj)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    vol = shepp3d(n)
+    ref = op.forward(vol)
+    got = be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1)
+    assert rel_l2(got, ref) <= TOL_PROJ
+    refb = op.adjoint(ref)
+    gotb = be.adjoint(torch.as_tensor(ref.astype(np.float32))).cpu().numpy().ravel()
+    assert rel_l2(gotb, refb) <= TOL_PROJ
+    # gradients of a subset of views at perturbed poses (what one alignment step evaluates)
+    sel = [0, 17, 44, 45, 89]
+    rec = (vol * 0.9).astype(np.float32)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T[sel] * np.array([1.0, 0.5, 0.5]), xyz[sel] * 0.5,
+                            g.cor_shift[sel]))
+    meas = torch.as_tensor(ref[sel].astype(np.float32))
+    out = be.proj_grad(torch.as_tensor(rec), meas=meas)
+    for k, i in enumerate(sel):
+        p, gr = O.forward_proj_grad(og, alpha[i] * 0.5, beta[i] * 0.5, phi[i], xyz[i] * 0.5, og.cor_shift[i], rec)
+        assert rel_l2(out["proj"][k].cpu().numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][k].cpu().numpy(), gr) <= TOL_GRAD, i
+        res = ref[i] - p
+        assert rel_l2(out["grad6"][k].cpu().numpy(), -gr @ res) <= TOL_GRAD, i
+
+
+def test_results_are_bitwise_deterministic():
+    g, og, be, op, _ = setup((48, 48, 48), (48, 48), 12, seed=3)
+    rng = np.random.default_rng(4)
+    vol = torch.as_tensor(rng.random((48, 48, 48)).astype(np.float32)).cuda()
+    y = torch.as_tensor(rng.random((12, 48 * 48)).astype(np.float32)).cuda()
+    f1, b1 = be.forward(vol).clone(), be.adjoint(y).clone()
+    g1 = be.proj_grad(vol, meas=y)
+    g1 = {k: v.clone() for k, v in g1.items()}
+    for _ in range(3):
+        assert torch.equal(be.forward(vol), f1) and torch.equal(be.adjoint(y), b1)
+        g2 = be.proj_grad(vol, meas=y)
+        assert torch.equal(g2["grad6"], g1["grad6"]) and torch.equal(g2["cost"], g1["cost"])
+        assert torch.equal(g2["dproj"], g1["dproj"])
+
+
+def test_adjointness_at_256cubed():
+    """Size-independent property at a BASELINE.json size: <A x, y> = <x, A^T y> (float64 dot products of the
+    float32 results), 256^3 with a handful of jittered views."""
+    n, n_proj = 256, 6
+    g, _ = make_geoms((n, n, n), (n, n), n_proj)
+    phi, alpha, beta, xyz = benchmark_poses(360)
+    sel = [0, 50, 123, 180, 271, 359]
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T[sel], xyz[sel], g.cor_shift))
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand((n, n, n), device="cuda", generator=gen)
+    y = torch.rand((n_proj, n, n), device="cuda", generator=gen)
+    lhs = torch.dot(be.forward(x).double().ravel(), y.double().ravel()).item()
+    rhs = torch.dot(x.double().ravel(), be.adjoint(y).double().ravel()).item()
+    assert abs(lhs - rhs) <= 2e-6 * abs(rhs)
+    # linearity of the forward projector
+    x2 = torch.rand((n, n, n), device="cuda", generator=gen)
+    lin = be.forward(x + 2 * x2) - (be.forward(x) + 2 * be.forward(x2))
+    assert lin.abs().max().item() <= 1e-4 * be.forward(x).abs().max().item()
+
+
+def test_phi0_projection_is_sum_over_y_at_256():
+    n = 256
+    g, _ = make_geoms((n, n, n), (n, n), 1)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([[0.0, 0.0, 0.0]]), np.zeros((1, 3)), np.zeros((1, 3))))
+    x = torch.rand((n, n, n), device="cuda")
+    p = be.forward(x)[0]
+    assert torch.allclose(p, x.double().sum(dim=1).float(), rtol=1e-5, atol=1e-4)
+
+
+def test_drop_in_operator_on_gpu_matches_reference_csr():
+    """ProjectionMatrix through the scipy idioms of recon/sirt.py, on the GPU, against the reference's CSR."""
+    g, og = make_geoms((12, 12, 12), (12, 12), 5)
+    phi, alpha, beta, xyz = random_poses(5, 9)
+    pm = ProjectionMatrix(g, precision=np.float32, device="cuda:0")
+    A = pm.projection_matrix(alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    R = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz).csr(np.float64)
+    rng = np.random.default_rng(0)
+    x, y = rng.random(g.n_vox).astype(np.float32), rng.random(5 * g.n_det).astype(np.float32)
+    ax = sparse.csr_matrix.dot(A, x)
+    aty = sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A), y)
+    assert isinstance(ax, np.ndarray) and isinstance(aty, np.ndarray)
+    assert rel_l2(ax, R @ x) <= TOL_PROJ and rel_l2(aty, R.T @ y) <= TOL_PROJ
+    xt = torch.as_tensor(x).cuda()
+    assert (A @ xt).is_cuda and rel_l2((A @ xt).cpu().numpy(), R @ x) <= TOL_PROJ
+    proj, grad = pm.projection_gradient(x.reshape(12, 12, 12), alpha[1], beta[1], phi[1], xyz[1], g.cor_shift[1])
+    p, gr = O.projection_gradient(og, x, alpha[1], beta[1], phi[1], xyz[1], og.cor_shift[1])
+    assert proj.dtype == np.float32 and grad.shape == (6, g.n_det)
+    assert rel_l2(proj, p) <= TOL_PROJ and rel_l2(grad, gr) <= TOL_GRAD
+
+
+def test_error_codes_surface_as_exceptions():
+    from tomography_alignment_b200 import _lib
+    g, _ = make_geoms((8, 8, 8), (8, 8), 2)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.zeros((2, 3)), np.zeros((2, 3)), np.zeros((2, 3))))
+    with pytest.raises(ValueError):
+        be.forward(torch.zeros(7))
+    with pytest.raises(ValueError):
+        be.adjoint(torch.zeros(5))
+    with pytest.raises(ValueError):
+        be.proj_grad(torch.zeros((8, 8, 8)), want_grad6=True)
+    with pytest.raises(_lib.TomoError):
+        _lib.check(be.lib.tomo_forward(be._g(), None, 2, None, None, None), "tomo_forward")

@@ -1,0 +1,93 @@
+"""Known-answer identities that pin the semantics of the live path."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from helpers import make_geoms, random_poses
+
+
+def test_phi0_projection_is_sum_over_y():
+    """phi = alpha = beta = 0, t = 0: samples sit at integer x, z and half-integer y, so
+    proj[ix, iz] = sum_y rec[ix, y, iz] exactly (both border half-weights included)."""
+    _, og = make_geoms((12, 10, 9), (12, 9), 1)
+    rec = np.random.default_rng(0).random((12, 10, 9))
+    op = O.OracleOperator(og, phi=np.array([0.0]))
+    np.testing.assert_allclose(op.forward(rec)[0].reshape(12, 9), rec.sum(axis=1), rtol=0, atol=1e-12)
+
+
+def test_adjointness():
+    _, og = make_geoms((10, 11, 12), (10, 12), 5, cor=[0.3, 0, 0])
+    phi, alpha, beta, xyz = random_poses(5, 1)
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    rng = np.random.default_rng(2)
+    x, y = rng.random(og.n_vox), rng.random((5, og.n_det))
+    assert abs(np.vdot(op.forward(x), y) - np.vdot(x, op.adjoint(y))) < 1e-10 * abs(np.vdot(x, op.adjoint(y)))
+
+
+def test_row_sums_are_chord_lengths():
+    """A 1 = in-volume chord length per ray: ny at phi = 0 (this is SIRT's W, recon/sirt.py:33)."""
+    _, og = make_geoms((8, 14, 8), (8, 8), 1)
+    op = O.OracleOperator(og, phi=np.array([0.0]))
+    np.testing.assert_allclose(op.forward(np.ones(og.n_vox))[0], 14.0, rtol=0, atol=1e-12)
+
+
+def test_gradient_matches_finite_differences():
+    """Central differences as in utilities/alignment_functions.py:225-241,424-445, on a smooth volume."""
+    _, og = make_geoms((14, 14, 14), (14, 14), 1)
+    c = np.arange(14) - 6.5
+    X, Y, Z = np.meshgrid(c, c, c, indexing="ij")
+    rec = np.exp(-(X ** 2 + 1.3 * Y ** 2 + 0.8 * Z ** 2) / 18.0)
+    th0 = np.array([0.21, -0.13, 0.33, 0.7, 0.012, -0.017])       # tx ty tz phi alpha beta
+
+    def proj(th):
+        p, _ = O.forward_proj_grad(og, th[4], th[5], th[3], th[:3], np.zeros(3), rec)
+        return p
+    _, g = O.forward_proj_grad(og, th0[4], th0[5], th0[3], th0[:3], np.zeros(3), rec)
+    for k in range(6):
+        e = np.zeros(6); e[k] = 1e-5
+        fd = (proj(th0 + e) - proj(th0 - e)) / 2e-5
+        # the interpolant is only piecewise smooth: compare in the L2 sense
+        assert np.linalg.norm(fd - g[k]) <= 2e-3 * max(np.linalg.norm(g[k]), 1.0), k
+
+
+def test_translation_along_beam_leaves_projection_unchanged():
+    """examples/generate_data.py:20-23: motion along the beam does not affect the projection -- as long
+    as no sample leaves the marching range.  ty shifts by an integer number of steps here."""
+    _, og = make_geoms((10, 10, 10), (10, 10), 1)
+    rec = np.random.default_rng(3).random((10, 10, 10))
+    a = O.OracleOperator(og, phi=np.array([0.0]), xyz_shift=np.array([[0.3, 0.0, -0.2]])).forward(rec)
+    b = O.OracleOperator(og, phi=np.array([0.0]), xyz_shift=np.array([[0.3, 2.0, -0.2]])).forward(rec)
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("w32", [False, True])
+def test_matrix_free_equals_reference_csr(w32):
+    """The reference's actual pipeline (COO -> CSR with duplicates summed, projection_operators.py:54-76)
+    against the matrix-free application."""
+    _, og = make_geoms((8, 9, 7), (8, 7), 4, cor=[0.25, 0, 0])
+    phi, alpha, beta, xyz = random_poses(4, 5)
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz, w32=w32)
+    A = op.csr(np.float32 if w32 else np.float64)
+    assert A.shape == (4 * og.n_det, og.n_vox)
+    rng = np.random.default_rng(6)
+    x, y = rng.random(og.n_vox), rng.random(4 * og.n_det)
+    tol = 2e-6 if w32 else 1e-12
+    np.testing.assert_allclose(A.astype(np.float64) @ x, op.forward(x).ravel(), rtol=tol, atol=tol)
+    np.testing.assert_allclose(A.astype(np.float64).T @ y, op.adjoint(y.reshape(4, -1)), rtol=tol, atol=tol)
+
+
+def test_csr_nnz_per_voxel_matches_survey():
+    """Sanity bound on the CSR size: at most 8 corners per sample and about one sample per voxel per view
+    (SURVEY.md section 6 quotes 7.3-7.9 per voxel before duplicates are merged at larger sizes)."""
+    _, og = make_geoms((16, 16, 16), (16, 16), 3)
+    phi, alpha, beta, xyz = random_poses(3, 8, shift=0.5, phis=[0.3, 1.0, 2.2])
+    A = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz).csr()
+    assert 3.0 < A.nnz / (3 * og.n_vox) < 8.5
+
+
+def test_shard_views_is_array_split():
+    for n, w in [(90, 8), (7, 3), (4, 8), (1500, 8)]:
+        parts = [O.shard_views(n, w, r) for r in range(w)]
+        assert np.array_equal(np.concatenate(parts), np.arange(n))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)

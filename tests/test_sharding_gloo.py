@@ -1,0 +1,78 @@
+"""Angle sharding + all-reduce over world_size-2 gloo on CPU (host logic of sharding.py; the per-rank
+operators are oracle-backed here).  Mirrors what recon/sirt_mpi.py:36-72,97-110 does with mpi4py."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+from helpers import OracleBackend, make_geoms, random_poses, rel_l2
+from tomography_alignment_b200.sharding import ShardedProjector, shard_views
+
+N_PROJ, SHAPE, DSHAPE = 5, (8, 8, 8), (8, 8)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, og = make_geoms(SHAPE, DSHAPE, N_PROJ, cor=np.array([[0.1 * i, 0, 0] for i in range(N_PROJ)]))
+        phi, alpha, beta, xyz = random_poses(N_PROJ, 21)
+        sp = ShardedProjector(g, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz, backend_factory=OracleBackend)
+        rng = np.random.default_rng(5)
+        vol = rng.random(SHAPE).astype(np.float32)
+        y = rng.random((N_PROJ, g.n_det)).astype(np.float32)
+        meas = rng.random((N_PROJ, g.n_det)).astype(np.float32)
+        mine = sp.my_index
+        proj = sp.forward(vol)
+        bp = sp.adjoint(torch.as_tensor(y[mine]))
+        n2 = sp.residual_norm2(torch.as_tensor(y[mine]))
+        pg = sp.proj_grad(vol, torch.as_tensor(meas[mine]))
+        out[rank] = dict(index=mine, proj=proj.numpy(), bp=bp.numpy(), n2=float(n2), grad6=pg["grad6_all"].numpy(),
+                         cost=pg["cost_all"].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_single_process():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    g, og = make_geoms(SHAPE, DSHAPE, N_PROJ, cor=np.array([[0.1 * i, 0, 0] for i in range(N_PROJ)]))
+    phi, alpha, beta, xyz = random_poses(N_PROJ, 21)
+    rng = np.random.default_rng(5)
+    vol = rng.random(SHAPE).astype(np.float32)
+    y = rng.random((N_PROJ, g.n_det)).astype(np.float32)
+    meas = rng.random((N_PROJ, g.n_det)).astype(np.float32)
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    ref_proj, ref_bp = op.forward(vol), op.adjoint(y)
+    # sharding follows np.array_split (sirt_mpi.py:40): rank 0 gets 3 views, rank 1 gets 2
+    assert list(out[0]["index"]) == [0, 1, 2] and list(out[1]["index"]) == [3, 4]
+    assert np.array_equal(np.concatenate([shard_views(N_PROJ, world, r) for r in range(world)]), np.arange(N_PROJ))
+    got_proj = np.concatenate([out[r]["proj"].reshape(len(out[r]["index"]), -1) for r in range(world)])
+    assert rel_l2(got_proj, ref_proj) < 1e-6
+    for r in range(world):                      # all-reduced quantities are replicated
+        assert rel_l2(out[r]["bp"], ref_bp) < 1e-6
+        assert abs(out[r]["n2"] - float((y.astype(np.float64) ** 2).sum())) < 1e-6 * float((y ** 2).sum())
+    g6 = np.zeros((N_PROJ, 6))
+    cost = np.zeros(N_PROJ)
+    for i in range(N_PROJ):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        res = meas[i].astype(np.float64) - p
+        g6[i], cost[i] = -gr @ res, 0.5 * res @ res
+    for r in range(world):
+        assert rel_l2(out[r]["grad6"], g6) < 1e-5 and rel_l2(out[r]["cost"], cost) < 1e-6
+    assert np.array_equal(out[0]["grad6"], out[1]["grad6"])

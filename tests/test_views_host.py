@@ -1,0 +1,72 @@
+"""tomo_views_compute_host (csrc/views.cpp) against the numpy setup of the oracle, which is checked
+bit for bit against the reference's numpy (test_oracle_golden.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tomography_alignment_b200 import _lib, pose_table
+from helpers import make_geoms, random_poses, _P
+
+V = dict(P00=0, U=3, W=6, D=9, N=12, RLEN=13, INVD=14, M=17, E=26, F=35, H=44, K=53, LINV=62, RB=71, VROT=74, VTR=83)
+
+
+def views_for(g, poses):
+    L = _lib.load()
+    out = np.zeros((poses.shape[0], _lib.VIEW_STRIDE))
+    cg = g.to_c()
+    _lib.check(L.tomo_views_compute_host(ctypes.byref(cg), _P(poses), poses.shape[0], _P(out)), "views")
+    return out
+
+
+@pytest.mark.parametrize("shape,dshape,cor,step", [((9, 8, 7), (9, 7), 0.0, 1.0), ((8, 8, 8), (10, 6), 0.6, 1.0),
+                                                   ((8, 8, 8), (8, 8), -0.3, 0.5)])
+def test_lattice_and_derivative_tables(shape, dshape, cor, step):
+    n_proj = 4
+    g, og = make_geoms(shape, dshape, n_proj, cor=[cor, 0, 0], step=step)
+    phi, alpha, beta, xyz = random_poses(n_proj, 11, tilt=0.1, phis=[0.0, 0.8, 1.9, np.pi])
+    views = views_for(g, pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    ix, iz = np.meshgrid(np.arange(dshape[0]), np.arange(dshape[1]), indexing="ij")
+    ix, iz = ix.ravel(), iz.ravel()
+    for i in range(n_proj):
+        vs = O.ViewSetup(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i])
+        v = views[i]
+        p0 = v[V["P00"]:V["P00"] + 3, None] + v[V["U"]:V["U"] + 3, None] * ix + v[V["W"]:V["W"] + 3, None] * iz
+        np.testing.assert_allclose(p0, vs.p0, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(v[V["D"]:V["D"] + 3, None] * np.ones_like(ix), vs.r_hat * vs.step_size, rtol=0, atol=1e-14)
+        assert int(v[V["N"]]) in (vs.n, vs.n + 1, vs.n - 1)       # int(r_length/step) sits on a rounding edge
+        assert abs(v[V["RLEN"]] - vs.r_length0) < 1e-12
+        der = vs.der()                                            # (9, 3, n_rays)
+        for k in range(3):
+            np.testing.assert_allclose(v[V["M"] + 3 * k:V["M"] + 3 * k + 3, None] * np.ones_like(ix), der[k], atol=1e-14)
+            e = v[V["E"] + 3 * k:V["E"] + 3 * k + 3, None] + v[V["F"] + 3 * k:V["F"] + 3 * k + 3, None] * ix \
+                + v[V["H"] + 3 * k:V["H"] + 3 * k + 3, None] * iz
+            np.testing.assert_allclose(e, der[3 + k], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(v[V["K"] + 3 * k:V["K"] + 3 * k + 3, None] * np.ones_like(ix),
+                                       der[6 + k] * vs.step_size / vs.r_length0, rtol=0, atol=1e-13)
+        Lm = np.array([v[V["U"]:V["U"] + 3], v[V["W"]:V["W"] + 3], v[V["D"]:V["D"] + 3]]).T
+        np.testing.assert_allclose(v[V["LINV"]:V["LINV"] + 9].reshape(3, 3) @ Lm, np.eye(3), atol=1e-12)
+        rot = O.rot_y(beta[i]) @ O.rot_x(alpha[i]) @ O.rot_z(phi[i])
+        np.testing.assert_allclose(v[V["VROT"]:V["VROT"] + 9].reshape(3, 3), rot, atol=1e-15)
+        np.testing.assert_allclose(v[V["VTR"]:V["VTR"] + 3], O.rot_y(beta[i]) @ xyz[i], atol=1e-15)
+
+
+def test_argument_errors_do_not_touch_cuda():
+    L = _lib.load()
+    g, _ = make_geoms((4, 4, 4), (4, 4), 1)
+    cg = g.to_c()
+    poses = np.zeros((1, 9))
+    out = np.zeros((1, _lib.VIEW_STRIDE))
+    assert L.tomo_views_compute_host(ctypes.byref(cg), None, 1, _P(out)) == -1
+    assert L.tomo_views_compute_host(ctypes.byref(cg), _P(poses), 0, _P(out)) == -1
+    cg.step_size = 0.0
+    assert L.tomo_views_compute_host(ctypes.byref(cg), _P(poses), 1, _P(out)) == -2
+    assert b"step_size" in L.tomo_last_error()
+    with pytest.raises(_lib.TomoError):
+        _lib.check(-2, "tomo_views_compute_host")
+    # null-pointer checks come before any CUDA call
+    assert L.tomo_forward(ctypes.byref(cg), None, 1, None, None, None) == -1
+    assert L.tomo_back_adjoint(ctypes.byref(cg), None, 1, None, None, 0, None) == -1
+    assert L.tomo_proj_grad(ctypes.byref(cg), None, 1, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.tomo_pad_volume(ctypes.byref(cg), None, None, None) == -1

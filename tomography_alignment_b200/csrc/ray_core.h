@@ -1,0 +1,251 @@
+// ray_core.h -- per-ray core of the ray-driven forward projector / gradient.
+//
+// __host__ __device__ so that tests/emu can run exactly this code on the CPU against the oracle
+// (test harness only; the product always runs it inside ray_kernels.cu on the GPU).
+//
+// What it computes, per ray (view, ix, iz):
+//   acc = sum_j trilinear(vol, p_j),   p_j = P00 + ix*U + iz*W + j*D          (ray_voxel_utilities.py:89-94,
+//                                                                             src/ray_wt_grad.f90:20-91)
+//   S0  = sum_j G_j,  S1 = sum_j j*G_j,  G = spatial gradient of the interpolant (src/ray_wt_grad.f90:142-220)
+// How:
+//   * the ray is clipped to the samples with -1 <= p < N on every axis (all others have no
+//     in-bounds corner); j keeps the reference's phase;
+//   * the volume is the zero-bordered copy (TOMO_PAD), so no per-corner bounds checks;
+//   * positions are carried as (cell offset, fraction): float32 fraction re-based from float64
+//     every RAY_REBASE samples for the forward projector, exact 64-bit fixed point for the gradient;
+//   * axes along which the ray runs backwards are mirrored (q = -p) so the carry is one-sided.
+#pragma once
+#include <math.h>
+#include "tomo_common.h"
+
+#ifdef __CUDACC__
+#define TOMO_HD __host__ __device__ __forceinline__
+#else
+#define TOMO_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define TOMO_LDG(p) __ldg(p)
+#else
+#define TOMO_LDG(p) (*(p))
+#endif
+
+#define RAY_REBASE 64
+
+struct RayDims {
+    int nx, ny, nz;      // volume shape
+    int sxp, syp;        // padded strides (floats) along x and y; z stride is 1
+};
+
+struct RaySums {
+    float acc;           // projection value
+    float s0[3], s1[3];  // gradient moments (real, un-mirrored coordinates)
+};
+
+// Clipped sample range and mirrored-frame constants of one ray.
+struct RaySetup {
+    double p[3], D[3];   // p0 of the ray and the step, voxel-index coordinates
+    int sg[3], st[3];    // mirror sign per axis, signed padded stride per axis
+    int j0, j1;          // samples j0 <= j < j1 can touch the volume
+    int stepoff;         // integer part of |D| (step_size > 1) folded into the address step
+};
+
+TOMO_HD void ray_setup(const double* __restrict__ V, const RayDims dm, int ix, int iz, RaySetup& r)
+{
+    const double N[3] = {(double)dm.nx, (double)dm.ny, (double)dm.nz};
+    const int ust[3] = {dm.sxp, dm.syp, 1};
+    double jlo = 0.0, jhi = V[V_N];
+    bool empty = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        r.p[a] = V[V_P00 + a] + (double)ix * V[V_U + a] + (double)iz * V[V_W + a];
+        r.D[a] = V[V_D + a];
+        // a sample has an in-bounds corner iff -1 < p < N on every axis
+        if (r.D[a] > 0.0) {
+            jlo = fmax(jlo, (-1.0 - r.p[a]) * V[V_INVD + a]);
+            jhi = fmin(jhi, (N[a] - r.p[a]) * V[V_INVD + a]);
+        } else if (r.D[a] < 0.0) {
+            jlo = fmax(jlo, (N[a] - r.p[a]) * V[V_INVD + a]);
+            jhi = fmin(jhi, (-1.0 - r.p[a]) * V[V_INVD + a]);
+        } else if (r.p[a] <= -1.0 || r.p[a] >= N[a]) {
+            empty = true;
+        }
+        r.sg[a] = (r.D[a] < 0.0) ? -1 : 1;
+        r.st[a] = r.sg[a] * ust[a];
+    }
+    // clamp in float64 first: 1/D is astronomically large for near-axis-parallel rays
+    jlo = fmin(fmax(jlo, 0.0), V[V_N]);
+    jhi = fmin(fmax(jhi, -1.0), V[V_N]);
+    r.j0 = (int)ceil(jlo);
+    r.j1 = (int)floor(jhi) + 1;
+    if (r.j1 > (int)V[V_N]) r.j1 = (int)V[V_N];
+    if (empty) r.j1 = r.j0;
+    r.stepoff = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) r.stepoff += (int)floor(fabs(r.D[a])) * r.st[a];
+}
+
+// Mirrored-frame cell and fraction of sample j on axis a, from float64:
+// q = sg*(p + j*D), cell = floor(q), frac = q - cell in [0, 1).
+TOMO_HD void ray_cell(const RaySetup& r, int a, int j, int ustride, int& off, double& frac)
+{
+    const double q = (double)r.sg[a] * (r.p[a] + (double)j * r.D[a]);
+    const double qi = floor(q);
+    frac = q - qi;
+    off += (TOMO_PAD + r.sg[a] * (int)qi) * ustride;
+}
+
+// frac (64-bit fixed point, hi:lo) += d; returns the carry out of bit 63.
+TOMO_HD unsigned fix64_add(unsigned& hi, unsigned& lo, unsigned dhi, unsigned dlo)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned c;
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;"
+        : "+r"(lo), "+r"(hi), "=r"(c) : "r"(dlo), "r"(dhi));
+    return c;
+#else
+    const unsigned long long f = ((unsigned long long)hi << 32) | lo, d = ((unsigned long long)dhi << 32) | dlo;
+    const unsigned long long s = f + d;
+    hi = (unsigned)(s >> 32); lo = (unsigned)s;
+    return s < f ? 1u : 0u;
+#endif
+}
+
+// top 23 bits of a 0.32 fixed-point fraction as a float in [0, 1)
+TOMO_HD float fix_to_float(unsigned hi)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__funnelshift_r(hi, 0x7Fu, 9)) - 1.0f;
+#else
+    union { unsigned u; float f; } c; c.u = 0x3f800000u | (hi >> 9); return c.f - 1.0f;
+#endif
+}
+
+// The 8 zero-padded corner loads and the trilinear interpolant in nested-lerp form; also returns the
+// pieces the spatial gradient is built from.
+#define RAY_SAMPLE(c, fx_, fy_, fz_)                                                                  \
+    const float v000 = TOMO_LDG(c),       v001 = TOMO_LDG(c + oz);                                      \
+    const float v010 = TOMO_LDG(c + o01), v011 = TOMO_LDG(c + o01 + oz);                                \
+    const float v100 = TOMO_LDG(c + o10), v101 = TOMO_LDG(c + o10 + oz);                                \
+    const float v110 = TOMO_LDG(c + o11), v111 = TOMO_LDG(c + o11 + oz);                                \
+    const float dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;        \
+    const float a00 = fmaf(fz_, dz00, v000), a01 = fmaf(fz_, dz01, v010);                              \
+    const float a10 = fmaf(fz_, dz10, v100), a11 = fmaf(fz_, dz11, v110);                              \
+    const float dy0 = a01 - a00, dy1 = a11 - a10;                                                      \
+    const float b0 = fmaf(fy_, dy0, a00), b1 = fmaf(fy_, dy1, a10);                                    \
+    const float gx = b1 - b0;                                                                          \
+    const float val = fmaf(fx_, gx, b0);
+
+// Forward only: (cell offset, float32 fraction) marching, re-based from float64 every RAY_REBASE
+// samples.  The interpolant is continuous, so a cell decision that is off by float32 rounding next
+// to a lattice plane changes nothing.
+TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                               int ix, int iz, RaySums& out)
+{
+    RaySetup r;
+    ray_setup(V, dm, ix, iz, r);
+    const int ust[3] = {dm.sxp, dm.syp, 1};
+    float df[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { const double ad = fabs(r.D[a]); df[a] = (float)(ad - floor(ad)); }
+    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1], oz = r.st[2];
+    float acc = 0.f;
+    for (int jc = r.j0; jc < r.j1; jc += RAY_REBASE) {
+        float f[3];
+        int off = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double fr;
+            ray_cell(r, a, jc, ust[a], off, fr);
+            f[a] = (float)fr;
+            if (f[a] >= 1.0f) { f[a] -= 1.0f; off += r.st[a]; }
+        }
+        const int jend = (jc + RAY_REBASE < r.j1) ? jc + RAY_REBASE : r.j1;
+        for (int j = jc; j < jend; ++j) {
+            const float* __restrict__ c = vol + off;
+            RAY_SAMPLE(c, f[0], f[1], f[2])
+            acc += val;
+            f[0] += df[0]; f[1] += df[1]; f[2] += df[2];
+            off += r.stepoff;
+            if (f[0] >= 1.0f) { f[0] -= 1.0f; off += r.st[0]; }
+            if (f[1] >= 1.0f) { f[1] -= 1.0f; off += r.st[1]; }
+            if (f[2] >= 1.0f) { f[2] -= 1.0f; off += r.st[2]; }
+        }
+    }
+    out.acc = acc;
+}
+
+// Projection + gradient moments.  The spatial gradient of the trilinear interpolant jumps across
+// lattice planes (one-sided differences, src/ray_wt_grad.f90:142-220), so the cell of every sample
+// must be the float64 one: the fraction is carried as 64-bit fixed point, which accumulates j*D
+// exactly (no re-basing, no branches); only the interpolation weights are rounded to float32.
+TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                                int ix, int iz, RaySums& out)
+{
+    RaySetup r;
+    ray_setup(V, dm, ix, iz, r);
+    const int ust[3] = {dm.sxp, dm.syp, 1};
+    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1], oz = r.st[2];
+    unsigned fh[3], fl[3], dh[3], dl[3];
+    int off = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double fr;
+        ray_cell(r, a, r.j0, ust[a], off, fr);
+        const unsigned long long f64 = (unsigned long long)(fr * 18446744073709551616.0);   // fr <= 1 - 2^-53
+        const double ad = fabs(r.D[a]);
+        const unsigned long long d64 = (unsigned long long)((ad - floor(ad)) * 18446744073709551616.0);
+        fh[a] = (unsigned)(f64 >> 32); fl[a] = (unsigned)f64;
+        dh[a] = (unsigned)(d64 >> 32); dl[a] = (unsigned)d64;
+    }
+    float acc = 0.f, s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+    float fj = (float)r.j0;
+    for (int j = r.j0; j < r.j1; ++j) {
+        const float fx = fix_to_float(fh[0]), fy = fix_to_float(fh[1]), fz = fix_to_float(fh[2]);
+        const float* __restrict__ c = vol + off;
+        RAY_SAMPLE(c, fx, fy, fz)
+        acc += val;
+        const float gy = fmaf(fx, dy1 - dy0, dy0);
+        const float e0 = fmaf(fy, dz01 - dz00, dz00), e1 = fmaf(fy, dz11 - dz10, dz10);
+        const float gz = fmaf(fx, e1 - e0, e0);
+        s0x += gx; s0y += gy; s0z += gz;
+        s1x = fmaf(fj, gx, s1x); s1y = fmaf(fj, gy, s1y); s1z = fmaf(fj, gz, s1z);
+        fj += 1.0f;
+        off += r.stepoff;
+        off += (int)fix64_add(fh[0], fl[0], dh[0], dl[0]) * r.st[0];
+        off += (int)fix64_add(fh[1], fl[1], dh[1], dl[1]) * r.st[1];
+        off += (int)fix64_add(fh[2], fl[2], dh[2], dl[2]) * r.st[2];
+    }
+    out.acc = acc;
+    out.s0[0] = s0x * (float)r.sg[0]; out.s0[1] = s0y * (float)r.sg[1]; out.s0[2] = s0z * (float)r.sg[2];
+    out.s1[0] = s1x * (float)r.sg[0]; out.s1[1] = s1y * (float)r.sg[1]; out.s1[2] = s1z * (float)r.sg[2];
+}
+
+template <bool GRAD>
+TOMO_HD void ray_march(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                       int ix, int iz, RaySums& out)
+{
+    if (GRAD) ray_march_gradient(vol, V, dm, ix, iz, out);
+    else      ray_march_forward(vol, V, dm, ix, iz, out);
+}
+
+// d proj / d theta_k for one ray, API order [tx, ty, tz, phi, alpha, beta]
+// (utilities/ray_voxel_utilities.py:37-48; src/ray_wt_grad.f90:136-141):
+//   d p_j / d t_k     = M[:,k]
+//   d p_j / d angle_k = E_k + ix F_k + iz H_k + j K_k
+TOMO_HD void ray_gradient(const double* __restrict__ V, int ix, int iz, const RaySums& s, float dp[6])
+{
+    const double S0[3] = {s.s0[0], s.s0[1], s.s0[2]}, S1[3] = {s.s1[0], s.s1[1], s.s1[2]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        dp[k] = (float)(S0[0] * V[V_M + 3 * k] + S0[1] * V[V_M + 3 * k + 1] + S0[2] * V[V_M + 3 * k + 2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double d = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double g0 = V[V_E + 3 * k + a] + (double)ix * V[V_F + 3 * k + a] + (double)iz * V[V_H + 3 * k + a];
+            d += S0[a] * g0 + S1[a] * V[V_K + 3 * k + a];
+        }
+        dp[3 + k] = (float)d;
+    }
+}

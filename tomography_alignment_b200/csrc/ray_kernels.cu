@@ -1,0 +1,226 @@
+// ray_kernels.cu -- ray-driven forward projector and projection + 6-DOF gradient, sm_100a.
+//
+// One thread owns one ray (view, ix, iz) and marches the samples p_j = p0 + j*D of
+// utilities/ray_voxel_utilities.py:89-94, evaluating the zero-padded trilinear interpolant of
+// src/ray_wt_grad.f90:20-91 (forward) and :121-222 (gradient).  Differences in *how* (not what):
+//   * nothing is materialised: p0 comes from the affine view record (tomo_common.h), the ray is
+//     clipped to the samples that can touch the volume, and the sample index j keeps the
+//     reference's phase so positions are identical;
+//   * the volume is read from a copy with a zero border of TOMO_PAD voxels, which realises the
+//     per-corner bounds checks of the Fortran without branches;
+//   * positions are carried as (integer cell, float32 fraction) with the fraction re-based from
+//     float64 every REBASE samples, so the interpolation weights carry ~1e-6 absolute error at any
+//     volume size instead of float32-at-coordinate-512 error;
+//   * axes along which the ray runs backwards are mirrored so the per-step carry is one-sided;
+//   * the gradient needs only S0 = sum_j G_j and S1 = sum_j j*G_j (G = spatial gradient of the
+//     interpolant) per ray, because d p_j / d theta is affine in j (ray_wt_grad.f90:136-141).
+// Lanes run along iz, the fastest detector axis, which maps to z, the fastest volume axis: corner
+// loads of a warp are contiguous for small tilts.  Blocks are ordered z-tile-major so that the
+// z-slab of the volume a tile row needs stays L2-resident while all views sweep over it.
+#include <cuda_runtime.h>
+#include "tomo_common.h"
+#include "ray_core.h"
+
+namespace {
+
+constexpr int TILE_Z = 32;     // lanes: iz
+constexpr int TILE_X = 8;      // warps: ix
+constexpr int NRED   = 7;      // 6 gradient components + cost
+
+struct RayArgs {
+    const float*  volpad;
+    const double* views;
+    const float*  meas;      // nullable
+    float*        proj;      // nullable
+    float*        dproj;     // nullable
+    double*       partial;   // nullable, [n_blocks][NRED]
+    int nx, ny, nz, ndx, ndz, n_proj;
+    int sxp, syp;            // padded strides (floats) of x and y; z stride is 1
+    int nxt, nzt;            // detector tiles along x and z
+};
+
+template <bool GRAD>
+__global__ void __launch_bounds__(TILE_Z * TILE_X)
+ray_kernel(const RayArgs A)
+{
+    const int bid  = blockIdx.x;
+    const int xt   = bid % A.nxt;
+    const int view = (bid / A.nxt) % A.n_proj;
+    const int zt   = bid / (A.nxt * A.n_proj);
+    const int iz = zt * TILE_Z + threadIdx.x;
+    const int ix = xt * TILE_X + threadIdx.y;
+    const bool active = (ix < A.ndx) && (iz < A.ndz);
+
+    const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+    const size_t n_det = (size_t)A.ndx * A.ndz;
+    const size_t ray = (size_t)ix * A.ndz + iz;
+
+    RaySums s;
+    s.acc = 0.f;
+    if (active) {
+        const RayDims dm = {A.nx, A.ny, A.nz, A.sxp, A.syp};
+        ray_march<GRAD>(A.volpad, V, dm, ix, iz, s);
+        if (A.proj) A.proj[(size_t)view * n_det + ray] = s.acc;
+    }
+
+    if (GRAD) {
+        double red[NRED] = {0, 0, 0, 0, 0, 0, 0};
+        if (active) {
+            float dp[6];
+            ray_gradient(V, ix, iz, s, dp);
+            if (A.dproj) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) A.dproj[((size_t)view * 6 + k) * n_det + ray] = dp[k];
+            }
+            if (A.meas) {
+                // residual and s.residual of utilities/alignment_functions.py:27-37,176-186
+                const double res = (double)A.meas[(size_t)view * n_det + ray] - (double)s.acc;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) red[k] = -(double)dp[k] * res;
+                red[6] = 0.5 * res * res;
+            }
+        }
+        if (A.partial) {       // fixed-order block reduction: shuffle tree, then warps in order
+            __shared__ double sm[TILE_X][NRED];
+#pragma unroll
+            for (int k = 0; k < NRED; ++k) {
+                double v = red[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (threadIdx.x == 0) sm[threadIdx.y][k] = v;
+            }
+            __syncthreads();
+            if (threadIdx.y == 0 && threadIdx.x < NRED) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < TILE_X; ++w) v += sm[w][threadIdx.x];
+                A.partial[(size_t)bid * NRED + threadIdx.x] = v;
+            }
+        }
+    }
+}
+
+// Second pass of the deterministic reduction: one thread per (view, component) sums the block
+// partials of that view in (zt, xt) order.
+__global__ void grad_finalize_kernel(const double* __restrict__ partial, int n_proj, int nxt, int nzt,
+                                     double* __restrict__ grad6, double* __restrict__ cost)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_proj * NRED) return;
+    const int view = t / NRED, k = t % NRED;
+    double v = 0.0;
+    for (int zt = 0; zt < nzt; ++zt)
+        for (int xt = 0; xt < nxt; ++xt)
+            v += partial[((size_t)(zt * n_proj + view) * nxt + xt) * NRED + k];
+    if (k < 6) { if (grad6) grad6[view * 6 + k] = v; }
+    else       { if (cost)  cost[view] = v; }
+}
+
+__global__ void pad_volume_kernel(const float* __restrict__ vol, float* __restrict__ pad,
+                                  int nx, int ny, int nz, int nyp, int nzp)
+{
+    // one thread per padded element, z fastest
+    const size_t total = (size_t)(nx + 2 * TOMO_PAD) * nyp * nzp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int zp = (int)(i % nzp);
+        const size_t r = i / nzp;
+        const int yp = (int)(r % nyp), xp = (int)(r / nyp);
+        const int x = xp - TOMO_PAD, y = yp - TOMO_PAD, z = zp - TOMO_PAD;
+        float v = 0.f;
+        if (x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz) v = vol[((size_t)x * ny + y) * nz + z];
+        pad[i] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" void tomo_set_error(const char* msg);
+int tomo_check_cuda(cudaError_t e, const char* what);
+
+static int check_sizes(const TomoGeom* g)
+{
+    const double padded = (double)(g->nx + 2 * TOMO_PAD) * (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz);
+    if (padded >= 2147483647.0) { tomo_set_error("padded volume exceeds 2^31 elements (32-bit kernel offsets)"); return TOMO_E_RANGE; }
+    return 0;
+}
+
+extern "C" size_t tomo_padded_volume_bytes(const TomoGeom* g)
+{
+    if (!g) return 0;
+    return sizeof(float) * (size_t)(g->nx + 2 * TOMO_PAD) * (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz);
+}
+
+extern "C" int tomo_pad_volume(const TomoGeom* g, const float* vol, float* pad, void* stream)
+{
+    if (!g || !vol || !pad) { tomo_set_error("tomo_pad_volume: null pointer"); return TOMO_E_ARG; }
+    if (int e = check_sizes(g)) return e;
+    const size_t total = tomo_padded_volume_bytes(g) / sizeof(float);
+    const int threads = 256;
+    const int blocks = (int)((total + threads - 1) / threads > 148 * 64 ? 148 * 64 : (total + threads - 1) / threads);
+    pad_volume_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(vol, pad, g->nx, g->ny, g->nz,
+                                                                     g->ny + 2 * TOMO_PAD, tomo_nzp(g->nz));
+    return tomo_check_cuda(cudaGetLastError(), "pad_volume_kernel");
+}
+
+static int fill_args(const TomoGeom* g, const void* views, int n_proj, const float* volpad, RayArgs* A)
+{
+    if (!g || !views || !volpad || n_proj <= 0) { tomo_set_error("ray operator: null pointer or n_proj <= 0"); return TOMO_E_ARG; }
+    if (int e = check_sizes(g)) return e;
+    A->volpad = volpad; A->views = (const double*)views;
+    A->meas = nullptr; A->proj = nullptr; A->dproj = nullptr; A->partial = nullptr;
+    A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz; A->n_proj = n_proj;
+    A->syp = tomo_nzp(g->nz);
+    A->sxp = (g->ny + 2 * TOMO_PAD) * A->syp;
+    A->nxt = (g->ndx + TILE_X - 1) / TILE_X;
+    A->nzt = (g->ndz + TILE_Z - 1) / TILE_Z;
+    const double nblocks = (double)A->nxt * A->nzt * n_proj;
+    if (nblocks >= 2147483647.0) { tomo_set_error("too many detector tiles for one launch"); return TOMO_E_RANGE; }
+    return 0;
+}
+
+extern "C" int tomo_forward(const TomoGeom* g, const void* views, int n_proj,
+                            const float* volpad, float* proj, void* stream)
+{
+    RayArgs A;
+    if (int e = fill_args(g, views, n_proj, volpad, &A)) return e;
+    if (!proj) { tomo_set_error("tomo_forward: proj_dev is NULL"); return TOMO_E_ARG; }
+    A.proj = proj;
+    const dim3 block(TILE_Z, TILE_X);
+    ray_kernel<false><<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+    return tomo_check_cuda(cudaGetLastError(), "ray_kernel<forward>");
+}
+
+extern "C" size_t tomo_proj_grad_workspace_bytes(const TomoGeom* g, int n_proj)
+{
+    if (!g || n_proj <= 0) return 0;
+    const size_t nxt = (g->ndx + TILE_X - 1) / TILE_X, nzt = (g->ndz + TILE_Z - 1) / TILE_Z;
+    return sizeof(double) * NRED * nxt * nzt * (size_t)n_proj;
+}
+
+extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
+                              const float* volpad, const float* meas,
+                              float* proj, float* dproj, double* grad6, double* cost,
+                              void* workspace, size_t workspace_bytes, void* stream)
+{
+    RayArgs A;
+    if (int e = fill_args(g, views, n_proj, volpad, &A)) return e;
+    A.meas = meas; A.proj = proj; A.dproj = dproj;
+    const bool reduce = (grad6 != nullptr) || (cost != nullptr);
+    if (reduce) {
+        if (!meas) { tomo_set_error("tomo_proj_grad: grad6/cost need meas_dev"); return TOMO_E_ARG; }
+        if (!workspace || workspace_bytes < tomo_proj_grad_workspace_bytes(g, n_proj)) {
+            tomo_set_error("tomo_proj_grad: workspace too small (see tomo_proj_grad_workspace_bytes)");
+            return TOMO_E_WORKSPACE;
+        }
+        A.partial = (double*)workspace;
+    }
+    const dim3 block(TILE_Z, TILE_X);
+    ray_kernel<true><<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+    if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel<gradient>")) return e;
+    if (reduce) {
+        const int n = n_proj * NRED;
+        grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, n_proj, A.nxt, A.nzt, grad6, cost);
+        return tomo_check_cuda(cudaGetLastError(), "grad_finalize_kernel");
+    }
+    return 0;
+}

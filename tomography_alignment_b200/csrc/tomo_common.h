@@ -1,0 +1,38 @@
+// tomo_common.h -- view-table layout and small helpers shared by host and device code.
+#pragma once
+#include <stdint.h>
+#include "../../include/tomo_b200.h"
+
+// Offsets (in doubles) into one view record of TOMO_VIEW_STRIDE doubles.
+// Sample lattice of a view (voxel-index coordinates, i.e. physical position minus vox_origin):
+//     p(ix, iz, j) = P00 + ix*U + iz*W + j*D ,   j = 0 .. n-1
+// which is p0 + j*step*r_hat of utilities/ray_voxel_utilities.py:74-94 with the affine dependence
+// of the source point on the detector pixel made explicit.
+enum {
+    V_P00  = 0,    // 3   lattice origin  M (Ry s00 + t) - vox_origin
+    V_U    = 3,    // 3   d p / d ix
+    V_W    = 6,    // 3   d p / d iz
+    V_D    = 9,    // 3   d p / d j = step_size * r_hat
+    V_N    = 12,   // 1   n = int(r_length / step_size)                    (ray_voxel_utilities.py:88)
+    V_RLEN = 13,   // 1   r_length of ray 0
+    V_INVD = 14,   // 3   1/D per axis (0 when D == 0)
+    V_M    = 17,   // 9   [k][a], k = tx,ty,tz: d p_a / d t_k = (Rz Rx)[a][k]  (ray_voxel_utilities.py:37-40)
+    V_E    = 26,   // 9   [k][a], k = phi,alpha,beta: pose derivative at ix = iz = 0, j = 0  (:42-45)
+    V_F    = 35,   // 9   [k][a]  its slope in ix
+    V_H    = 44,   // 9   [k][a]  its slope in iz
+    V_K    = 53,   // 9   [k][a]  its slope in j: der[6+k] * step_size / r_length   (:46-48, :148-151)
+    V_LINV = 62,   // 9   row-major inverse of L = [U W D]: lattice coords (ix, iz, j) = Linv (p - P00)
+    V_RB   = 71,   // 3   candidate half-widths in lattice coords: sum_a |Linv[k][a]|
+    V_VROT = 74,   // 9   row-major Ry(b) Rx(a) Rz(p)      (src/external_back_projection.f90:17-25)
+    V_VTR  = 83,   // 3   Ry(b) t
+    V_END  = 86
+};
+
+static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");
+
+// Row pitch (floats) of the padded volume along z.
+static inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int tomo_nzp(int nz) { return ((nz + 2 * TOMO_PAD + 31) / 32) * 32; }

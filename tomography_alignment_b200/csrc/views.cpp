@@ -1,0 +1,148 @@
+// views.cpp -- host-side, float64 per-view constants (no CUDA).
+//
+// Restates the numpy setup the reference performs for every view before it calls its Fortran
+// kernels, reduced to closed form:
+//   rotations                  utilities/rotations.py:9-48
+//   transform_points           utilities/ray_voxel_utilities.py:6-12     Rz(phi) Rx(alpha) (Ry(beta) x + t)
+//   source/detector grids      utilities/geometry.py:90-100              s = (xd + cor_x, -sy, zd)
+//   ray marching               utilities/ray_voxel_utilities.py:74-94    p_j = p0 + j*step*r_hat, n = int(|r|/step)
+//   derivative_ray_points      utilities/ray_voxel_utilities.py:15-50    (9,3,n_rays) table
+// Because the source grid is affine in the detector pixel (ix, iz), every per-ray quantity the
+// reference tabulates is affine in (ix, iz); this file computes the affine coefficients.
+#include <cmath>
+#include <cstring>
+#include "tomo_common.h"
+
+namespace {
+
+struct M3 { double m[3][3]; };
+struct V3 { double v[3]; };
+
+M3 rot_z(double a)  { return {{{std::cos(a), -std::sin(a), 0.}, {std::sin(a), std::cos(a), 0.}, {0., 0., 1.}}}; }
+M3 drot_z(double a) { return {{{-std::sin(a), -std::cos(a), 0.}, {std::cos(a), -std::sin(a), 0.}, {0., 0., 0.}}}; }
+M3 rot_x(double a)  { return {{{1., 0., 0.}, {0., std::cos(a), -std::sin(a)}, {0., std::sin(a), std::cos(a)}}}; }
+M3 drot_x(double a) { return {{{0., 0., 0.}, {0., -std::sin(a), -std::cos(a)}, {0., std::cos(a), -std::sin(a)}}}; }
+M3 rot_y(double a)  { return {{{std::cos(a), 0., std::sin(a)}, {0., 1., 0.}, {-std::sin(a), 0., std::cos(a)}}}; }
+M3 drot_y(double a) { return {{{-std::sin(a), 0., std::cos(a)}, {0., 0., 0.}, {-std::cos(a), 0., -std::sin(a)}}}; }
+
+M3 mul(const M3& a, const M3& b) {
+    M3 c;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+        c.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+    return c;
+}
+V3 mul(const M3& a, const V3& x) {
+    V3 y;
+    for (int i = 0; i < 3; ++i) y.v[i] = a.m[i][0] * x.v[0] + a.m[i][1] * x.v[1] + a.m[i][2] * x.v[2];
+    return y;
+}
+V3 add(const V3& a, const V3& b) { return {{a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2]}}; }
+V3 sub(const V3& a, const V3& b) { return {{a.v[0] - b.v[0], a.v[1] - b.v[1], a.v[2] - b.v[2]}}; }
+void put(double* dst, const V3& a) { dst[0] = a.v[0]; dst[1] = a.v[1]; dst[2] = a.v[2]; }
+
+}  // namespace
+
+extern "C" void tomo_set_error(const char* msg);
+
+extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, int n_proj, double* out)
+{
+    if (!g || !poses || !out || n_proj <= 0) { tomo_set_error("tomo_views_compute_host: null pointer or n_proj <= 0"); return TOMO_E_ARG; }
+    if (!(g->step_size > 0.0) || g->nx <= 0 || g->ny <= 0 || g->nz <= 0 || g->ndx <= 0 || g->ndz <= 0 ||
+        !(g->det_y != g->src_y)) {
+        tomo_set_error("tomo_views_compute_host: invalid geometry (sizes must be > 0, step_size > 0, det_y != src_y)");
+        return TOMO_E_GEOM;
+    }
+    const V3 org = {{g->vox_origin[0], g->vox_origin[1], g->vox_origin[2]}};
+    for (int v = 0; v < n_proj; ++v) {
+        const double* ps = poses + (size_t)v * TOMO_POSE_STRIDE;
+        double* o = out + (size_t)v * TOMO_VIEW_STRIDE;
+        std::memset(o, 0, sizeof(double) * TOMO_VIEW_STRIDE);
+        const double phi = ps[0], alpha = ps[1], beta = ps[2];
+        const V3 t = {{ps[3], ps[4], ps[5]}};
+        const double cor_x = ps[6];
+
+        const M3 Rp = rot_z(phi), Ra = rot_x(alpha), Rb = rot_y(beta);
+        const M3 dRp = drot_z(phi), dRa = drot_x(alpha), dRb = drot_y(beta);
+        const M3 Rpa = mul(Rp, Ra);             // rot_pa, ray_voxel_utilities.py:8
+        const M3 Rab = mul(Ra, Rb);             // R_ab,   ray_voxel_utilities.py:32
+
+        // source / detector point of ray (0,0) with the centre-of-rotation shift applied to x
+        // (ray_voxel_utilities.py:72-73), and the grid steps
+        const V3 s00 = {{g->det_x0 + cor_x, g->src_y, g->det_z0}};
+        const V3 d00 = {{g->det_x0 + cor_x, g->det_y, g->det_z0}};
+        const V3 ex = {{g->det_dx, 0., 0.}}, ez = {{0., 0., g->det_dz}};
+
+        const V3 Rb_s00_t = add(mul(Rb, s00), t);                  // Ry s + t
+        const V3 p0 = sub(mul(Rpa, Rb_s00_t), org);                // :74
+        const V3 p1 = sub(mul(Rpa, add(mul(Rb, d00), t)), org);    // :75
+        const V3 U = mul(Rpa, mul(Rb, ex));
+        const V3 W = mul(Rpa, mul(Rb, ez));
+        const V3 r = sub(p1, p0);
+        const double rlen = std::sqrt(r.v[0] * r.v[0] + r.v[1] * r.v[1] + r.v[2] * r.v[2]);   // :86
+        const V3 rhat = {{r.v[0] / rlen, r.v[1] / rlen, r.v[2] / rlen}};
+        const int n = (int)(rlen / g->step_size);                  // :88 (truncation)
+        const V3 D = {{g->step_size * rhat.v[0], g->step_size * rhat.v[1], g->step_size * rhat.v[2]}};
+
+        put(o + V_P00, p0); put(o + V_U, U); put(o + V_W, W); put(o + V_D, D);
+        o[V_N] = (double)n; o[V_RLEN] = rlen;
+        for (int a = 0; a < 3; ++a) o[V_INVD + a] = (D.v[a] != 0.0) ? 1.0 / D.v[a] : 0.0;
+
+        // translations: der[k] = (Rz Rx)[:, k]                    (:37-40)
+        for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) o[V_M + 3 * k + a] = Rpa.m[a][k];
+
+        // angles, order phi, alpha, beta                          (:42-45)
+        const M3 A3 = mul(dRp, Ra);     // dRz Rx   applied to (Ry s + t)
+        const M3 A4 = mul(Rp, dRa);     // Rz dRx   applied to (Ry s + t)
+        const M3 A5 = mul(Rpa, dRb);    // Rz Rx dRy applied to s
+        put(o + V_E + 0, mul(A3, Rb_s00_t));
+        put(o + V_F + 0, mul(A3, mul(Rb, ex)));
+        put(o + V_H + 0, mul(A3, mul(Rb, ez)));
+        put(o + V_E + 3, mul(A4, Rb_s00_t));
+        put(o + V_F + 3, mul(A4, mul(Rb, ex)));
+        put(o + V_H + 3, mul(A4, mul(Rb, ez)));
+        put(o + V_E + 6, mul(A5, s00));
+        put(o + V_F + 6, mul(A5, ex));
+        put(o + V_H + 6, mul(A5, ez));
+
+        // step-dependent parts on the untransformed ray vector d - s of ray 0   (:46-48), scaled by
+        // d step / d j = step_size / r_length                                    (:148-151)
+        const V3 rv = sub(d00, s00);
+        const double sc = g->step_size / rlen;
+        const V3 k3 = mul(dRp, mul(Rab, rv));
+        const V3 k4 = mul(Rp, mul(dRa, mul(Rb, rv)));
+        const V3 k5 = mul(Rpa, mul(dRb, rv));
+        for (int a = 0; a < 3; ++a) {
+            o[V_K + 0 + a] = k3.v[a] * sc;
+            o[V_K + 3 + a] = k4.v[a] * sc;
+            o[V_K + 6 + a] = k5.v[a] * sc;
+        }
+
+        // inverse lattice map for the gather backprojector
+        const double L[3][3] = {{U.v[0], W.v[0], D.v[0]}, {U.v[1], W.v[1], D.v[1]}, {U.v[2], W.v[2], D.v[2]}};
+        const double det = L[0][0] * (L[1][1] * L[2][2] - L[1][2] * L[2][1])
+                         - L[0][1] * (L[1][0] * L[2][2] - L[1][2] * L[2][0])
+                         + L[0][2] * (L[1][0] * L[2][1] - L[1][1] * L[2][0]);
+        if (!(std::fabs(det) > 0.0)) { tomo_set_error("tomo_views_compute_host: degenerate sample lattice"); return TOMO_E_GEOM; }
+        const double id = 1.0 / det;
+        double Li[3][3];
+        Li[0][0] =  (L[1][1] * L[2][2] - L[1][2] * L[2][1]) * id;
+        Li[0][1] = -(L[0][1] * L[2][2] - L[0][2] * L[2][1]) * id;
+        Li[0][2] =  (L[0][1] * L[1][2] - L[0][2] * L[1][1]) * id;
+        Li[1][0] = -(L[1][0] * L[2][2] - L[1][2] * L[2][0]) * id;
+        Li[1][1] =  (L[0][0] * L[2][2] - L[0][2] * L[2][0]) * id;
+        Li[1][2] = -(L[0][0] * L[1][2] - L[0][2] * L[1][0]) * id;
+        Li[2][0] =  (L[1][0] * L[2][1] - L[1][1] * L[2][0]) * id;
+        Li[2][1] = -(L[0][0] * L[2][1] - L[0][1] * L[2][0]) * id;
+        Li[2][2] =  (L[0][0] * L[1][1] - L[0][1] * L[1][0]) * id;
+        for (int k = 0; k < 3; ++k) {
+            for (int a = 0; a < 3; ++a) o[V_LINV + 3 * k + a] = Li[k][a];
+            o[V_RB + k] = std::fabs(Li[k][0]) + std::fabs(Li[k][1]) + std::fabs(Li[k][2]);
+        }
+
+        // voxel-driven (inverse convention) transform  Ry (Rx Rz x + t)   (external_back_projection.f90:17-25)
+        const M3 Vr = mul(Rb, mul(Ra, Rp));
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[V_VROT + 3 * i + j] = Vr.m[i][j];
+        put(o + V_VTR, mul(Rb, t));
+    }
+    return 0;
+}

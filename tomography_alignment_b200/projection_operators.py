@@ -1,0 +1,223 @@
+"""Drop-in for the reference's ``utilities/projection_operators.py`` (the L2 operator API).
+
+``ProjectionMatrix`` keeps the reference's constructor and the signatures, defaults and side effects
+of ``projection_matrix`` (utilities/projection_operators.py:22-76) and ``projection_gradient``
+(:112-122).  Instead of a scipy CSR matrix (7.5*n_vox*n_proj non-zeros: 5.4 TiB at 512^3 x 720),
+``projection_matrix`` returns a matrix-free ``ProjectionOperator`` that survives every way the
+reference's solvers use the matrix:
+
+    sparse.csr_matrix.dot(A, x)                                   recon/sirt.py:59, cgls.py:72
+    sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A), y)      recon/sirt.py:61, cgls.py:54
+    A.shape
+
+numpy in -> numpy out (host<->device copies inside the call, like a scipy matvec on host arrays);
+torch CUDA tensor in -> torch CUDA tensor out (no copies; what device-resident solvers and
+bench.py's kernel timing use).  All arithmetic runs in libtomo_b200.so on the GPU; there is no CPU
+path -- without CUDA, applying the operator raises.
+"""
+import numpy as np
+
+try:
+    import torch
+except ImportError:  # pragma: no cover - torch is part of the image
+    torch = None
+
+
+def normalise_poses(geometry, alpha=None, beta=None, phi=None, xyz_shift=None):
+    """Argument handling of ProjectionMatrix.projection_matrix, utilities/projection_operators.py:24-52.
+
+    Returns (n_proj, angles (n_proj, 3) = [phi, alpha, beta], xyz_shift (n_proj, 3))."""
+    if phi is None:
+        n_proj = geometry.n_proj
+        phi = np.linspace(0., np.pi, n_proj)
+    else:
+        n_proj = np.size(phi)
+    if alpha is None:
+        alpha = np.zeros_like(phi)
+    if beta is None:
+        beta = np.zeros_like(phi)
+    if xyz_shift is None:
+        xyz_shift = np.zeros((n_proj, 3))
+    phi = np.squeeze(phi)
+    alpha = np.squeeze(alpha)
+    beta = np.squeeze(beta)
+    xyz_shift = np.squeeze(xyz_shift)
+    if n_proj == 1:
+        phi = np.array([phi])
+        alpha = np.array([alpha])
+        beta = np.array([beta])
+        xyz_shift = np.array([xyz_shift])
+    angles = np.array([phi, alpha, beta]).T
+    return n_proj, angles, xyz_shift
+
+
+def pose_table(angles, xyz_shift, cor_shift):
+    """(n_proj, 9) float64 rows [phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z] for the C ABI."""
+    angles = np.asarray(angles, dtype=np.float64).reshape(-1, 3)
+    n = angles.shape[0]
+    poses = np.zeros((n, 9), dtype=np.float64)
+    poses[:, 0:3] = angles
+    poses[:, 3:6] = np.asarray(xyz_shift, dtype=np.float64).reshape(n, 3)
+    poses[:, 6:9] = np.asarray(cor_shift, dtype=np.float64).reshape(n, 3)
+    return poses
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class ProjectionOperator(object):
+    """Matrix-free A (or A^T) of shape (n_proj*n_det, n_vox) ((n_vox, n_proj*n_det) transposed).
+
+    Duck-types the parts of scipy's csr/csc matrices the reference's solvers touch through unbound
+    methods: ``ndim``, ``shape``, ``data``/``indices``/``indptr`` (placeholders) and
+    ``_csc_container`` for ``sparse.csr_matrix.transpose``; ``__matmul__`` for ``_spbase.dot``.
+    """
+    ndim = 2
+
+    def __init__(self, backend, n_proj, n_det, n_vox, precision=np.float32, voxel_mask=None,
+                 transposed=False, all_masked=False):
+        self._backend = backend
+        self._n_proj, self._n_det, self._n_vox = int(n_proj), int(n_det), int(n_vox)
+        self._transposed = bool(transposed)
+        self._precision = precision
+        self._mask = voxel_mask          # bool ndarray (n_vox,) or None
+        self._mask_dev = None
+        self._all_masked = all_masked
+        rows, cols = self._n_proj * self._n_det, self._n_vox
+        self.shape = (cols, rows) if transposed else (rows, cols)
+        self.dtype = np.dtype(precision)
+        # placeholders read by sparse.csr_matrix.transpose before it calls _csc_container
+        self.data = self.indices = self.indptr = None
+
+    # -- scipy unbound-method idioms -------------------------------------------------------------
+    def _csc_container(self, arg1, shape=None, copy=False):
+        return self.transpose()
+
+    _csr_container = _csc_container
+
+    def transpose(self, axes=None, copy=False):
+        return ProjectionOperator(self._backend, self._n_proj, self._n_det, self._n_vox, self._precision,
+                                  self._mask, not self._transposed, self._all_masked)
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    def dot(self, other):
+        return self.__matmul__(other)
+
+    def __matmul__(self, other):
+        return self._rmatvec(other) if self._transposed else self._matvec(other)
+
+    def matvec(self, x):
+        return self.__matmul__(x)
+
+    def rmatvec(self, y):
+        return self.transpose().__matmul__(y)
+
+    # -- application -----------------------------------------------------------------------------
+    def _mask_on(self, like):
+        if self._mask_dev is None:
+            self._mask_dev = torch.as_tensor(self._mask.astype(np.float32), device=like.device)
+        return self._mask_dev
+
+    def _matvec(self, x):
+        if np.size(x) != self._n_vox:
+            raise ValueError("dimension mismatch: operator has %d columns, vector has %d entries"
+                             % (self._n_vox, np.size(x)))
+        was_torch = _is_torch(x)
+        xd = self._backend._as_vol(x if was_torch else np.ascontiguousarray(np.asarray(x), dtype=np.float32))
+        if self._mask is not None:
+            # dropping the masked columns' entries (projection_operators.py:60-70) == zeroing x there
+            xd = xd.reshape(-1) * (0.0 if self._all_masked else self._mask_on(xd))
+        y = self._backend.forward(xd).reshape(-1)
+        if was_torch:
+            return y
+        return y.cpu().numpy().astype(np.result_type(self._precision, np.asarray(x).dtype), copy=False)
+
+    def _rmatvec(self, y):
+        if np.size(y) != self._n_proj * self._n_det:
+            raise ValueError("dimension mismatch: operator has %d rows, vector has %d entries"
+                             % (self._n_proj * self._n_det, np.size(y)))
+        was_torch = _is_torch(y)
+        yd = self._backend._as_proj(y if was_torch else np.ascontiguousarray(np.asarray(y), dtype=np.float32))
+        v = self._backend.adjoint(yd).reshape(-1)
+        if self._mask is not None:
+            v = v * (0.0 if self._all_masked else self._mask_on(v))
+        if was_torch:
+            return v
+        return v.cpu().numpy().astype(np.result_type(self._precision, np.asarray(y).dtype), copy=False)
+
+
+class ProjectionMatrix(object):
+    """Same interface as the reference's class (utilities/projection_operators.py:11-122).
+
+    ``backend`` is for tests that exercise the host logic without a GPU; by default the CUDA backend
+    is created on first use and raises if no CUDA device is present."""
+
+    def __init__(self, geometry, precision=np.float32, device=None, backend=None):
+        self.geometry = geometry
+        self.precision = precision
+        self.n_proj = None
+        self.angles = None
+        self.xyz_shift = None
+        self.voxel_mask = None
+        self._device = device
+        self._backend = backend
+        self._grad_backend = None
+
+    def _get_backend(self):
+        if self._backend is None:
+            from .cuda_backend import CudaBackend
+            self._backend = CudaBackend(self.geometry, self._device)
+        return self._backend
+
+    def projection_matrix(self, alpha=None, beta=None, phi=None, xyz_shift=None, voxel_mask=None):
+        self.n_proj, self.angles, self.xyz_shift = normalise_poses(self.geometry, alpha, beta, phi, xyz_shift)
+        self.voxel_mask = voxel_mask
+        cor = np.asarray(self.geometry.cor_shift, dtype=np.float64)
+        if cor.ndim == 1:      # a geometry whose cor_shift was replaced by one row (sirt_mpi.py:46-47 does this)
+            cor = np.tile(cor, self.n_proj).reshape(self.n_proj, 3)
+        poses = pose_table(self.angles, self.xyz_shift, cor[:self.n_proj])
+        backend = self._get_backend()
+        backend.set_poses(poses)
+        mask, all_masked = None, False
+        if voxel_mask is not None:
+            mask = np.asarray(voxel_mask).ravel().astype(bool)
+            if np.sum(mask) == 0:
+                print('entire object is masked')     # projection_operators.py:63-65
+                all_masked = True
+        return ProjectionOperator(backend, self.n_proj, self.geometry.n_det, self.geometry.n_vox,
+                                  self.precision, mask, False, all_masked)
+
+    def projection_gradient(self, rec, alpha, beta, phi, xyz_shift, cor_shift):
+        """One view: (proj (n_det,), grad (6, n_det)), gradient rows [tx, ty, tz, phi, alpha, beta]
+        (utilities/projection_operators.py:112-122, utilities/ray_voxel_utilities.py:39-46)."""
+        out = self.projection_gradient_batch(rec, np.array([[phi, alpha, beta]], dtype=np.float64),
+                                             np.asarray(xyz_shift, dtype=np.float64).reshape(1, 3),
+                                             np.asarray(cor_shift, dtype=np.float64).reshape(-1)[:3].reshape(1, 3))
+        proj, grad = out["proj"].reshape(-1), out["dproj"].reshape(6, -1)
+        if _is_torch(rec):
+            return proj, grad
+        return (proj.cpu().numpy().astype(self.precision, copy=False),
+                grad.cpu().numpy().astype(self.precision, copy=False))
+
+    def projection_gradient_batch(self, rec, angles, xyz_shift, cor_shift=None, meas=None,
+                                  want_dproj=True, want_proj=True):
+        """All views at once on the device (what the reference does with n_proj separate calls,
+        examples/align_rigid.py:40-49).  angles (n, 3) = [phi, alpha, beta].  With ``meas`` also
+        returns grad6 (n, 6) = sum_rays (-dproj) * (meas - proj) and cost (n,) = 0.5*||meas - proj||^2,
+        i.e. gradient_* / cost_* of utilities/alignment_functions.py before parameter masking."""
+        if self._grad_backend is None:
+            if self._backend is not None and not hasattr(self._backend, "views"):
+                self._grad_backend = self._backend          # injected test backend
+            else:
+                from .cuda_backend import CudaBackend
+                self._grad_backend = CudaBackend(self.geometry, self._device)
+        angles = np.asarray(angles, dtype=np.float64).reshape(-1, 3)
+        n = angles.shape[0]
+        if cor_shift is None:
+            cor_shift = np.asarray(self.geometry.cor_shift, dtype=np.float64).reshape(-1, 3)[:n]
+        self._grad_backend.set_poses(pose_table(angles, xyz_shift, cor_shift))
+        return self._grad_backend.proj_grad(rec, meas=meas, want_proj=want_proj, want_dproj=want_dproj)
