@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the projection hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--views 720] [--impl b200|reference]
+
+One *step* = one forward projection of all views + one exact-adjoint backprojection of all views + one
+projection-and-6-DOF-gradient pass over all views (SURVEY.md section 8d "s per alignment iter") of a
+Shepp-Logan phantom with the jittered poses of examples/generate_data.py (seeded).  The unit of work is the
+voxel-ray update: n_vox * n_proj per operator, 3 operators per step.
+
+N > 1 (launched by torchrun, one rank per GPU): the views are sharded across ranks with
+np.array_split (recon/sirt_mpi.py:40), the volume is replicated, the backprojected volume is summed with an
+NCCL all-reduce and the per-view gradient table assembled with a zero-padded all-reduce; the total problem is
+fixed (strong scaling).
+
+Output: ONE JSON line on rank 0 (see the keys at the bottom).  `value` times device-resident inputs with CUDA
+events; `e2e` times the same three operators through the public ProjectionMatrix API with pinned HOST
+buffers, host<->device copies inside the timed region.
+--impl reference times the CPU oracle port of the reference's loops on the host cores (the reference's own
+Fortran cannot be built here: no gfortran).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxel-ray updates/s fwd+back+grad"
+UNIT = "voxel-ray updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--views", type=int, default=720)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-size", type=int, default=256, help="volume size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "%d^3 x %d views, fwd + adjoint back + 6-DOF grad" % (a.size, a.views)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU leg (oracle port): cpu_baseline of the b200 arm and the whole --impl reference arm
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(cpu_size, target_s=12.0):
+    """Time fwd+back+grad of the oracle port on a bounded sample: cpu_size^3, one view per worker at a time,
+    all host cores (capped at 64 workers: each keeps a private float64 volume, 128 MiB at 256^3)."""
+    from oracle import oracle as O
+    from tomography_alignment_b200.phantom import benchmark_poses
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    # calibrate on one view per worker, then size the sample for ~target_s seconds
+    dt, upd = O.cpu_fwd_back_grad(cpu_size, workers, workers, benchmark_poses(workers))
+    rounds = int(max(1, min(8, target_s / max(dt, 1e-3))))
+    if rounds > 1:
+        n_views = workers * rounds
+        dt, upd = O.cpu_fwd_back_grad(cpu_size, n_views, workers, benchmark_poses(n_views))
+    else:
+        n_views = workers
+    return {"value": upd / dt, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": "%d^3 x %d views fwd+back+grad, views split over %d threads (np.array_split as in "
+                      "recon/*_mpi.py), C port of src/ray_wt_grad.f90 loops at -O3, %.1f s"
+                      % (cpu_size, n_views, workers, dt)}, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    info = None
+    for i in range(a.warmup + a.steps):
+        info, dt = cpu_sample(a.cpu_size, target_s=6.0)
+        if i >= a.warmup:
+            per_step.append((info["value"], dt))
+    val = float(np.mean([v for v, _ in per_step]))
+    ms = float(np.mean([d for _, d in per_step])) * 1e3
+    info["value"] = val
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "each step is the bounded CPU sample described in "
+                       "cpu_baseline.sample; throughput is size-independent to first order"},
+            "cpu_baseline": info,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from tomography_alignment_b200 import Geometry, ProjectionMatrix, pose_table
+    from tomography_alignment_b200.cuda_backend import CudaBackend
+    from tomography_alignment_b200.phantom import benchmark_poses, shepp3d
+    from tomography_alignment_b200.sharding import shard_views
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, n_proj = a.size, a.views
+    geo = Geometry(n_proj, np.array([n, n, n]), np.ones(3), np.array([n, n]), np.ones(2))
+    phi, alpha, beta, xyz = benchmark_poses(n_proj)
+    mine = shard_views(n_proj, world, rank)
+    my_n = len(mine)
+    poses = pose_table(np.array([phi, alpha, beta]).T, xyz, geo.cor_shift)
+    # "true" poses generate the measured data; the current estimate (half the jitter) is what fwd/grad use
+    be_true = CudaBackend(geo, dev)
+    be_true.set_poses(poses[mine])
+    est = poses.copy()
+    est[:, 1:3] *= 0.5
+    est[:, 3:6] *= 0.5
+    be = CudaBackend(geo, dev)
+    be.set_poses(est[mine])
+
+    vol_true = shepp3d(n, device=dev)
+    meas = be_true.forward(vol_true).clone()              # b = A_true phantom, (my_n, n, n)
+    vol = (0.9 * vol_true).contiguous()                    # current reconstruction estimate
+    proj = torch.empty_like(meas)
+    bp = torch.empty((n, n, n), dtype=torch.float32, device=dev)
+    table = torch.zeros((n_proj, 7), dtype=torch.float64, device=dev)
+    idx = torch.as_tensor(mine, device=dev, dtype=torch.long)
+    del be_true
+    torch.cuda.synchronize()
+
+    n_vox, n_det = float(n) ** 3, float(n) ** 2
+    updates_per_step = 3.0 * n_vox * n_proj
+
+    def step():
+        be.forward(vol, out=proj)                                   # pad + forward, all local views
+        res = meas - proj                                            # residual (elementwise, torch)
+        be.adjoint(res, out=bp)                                      # exact adjoint, all local views
+        if world > 1:
+            dist.all_reduce(bp)
+        out = be.proj_grad(vol, meas=meas, want_proj=False, want_dproj=False, repad=False)
+        if world > 1:
+            table.zero_()
+            table[idx, :6] = out["grad6"]
+            table[idx, 6] = out["cost"]
+            dist.all_reduce(table)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    sync_all()
+    launches0 = be.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = be.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / a.steps
+    value = updates_per_step / (ms_per_step * 1e-3)
+
+    # per-kernel timing for the roofline of the dominant kernel (rank 0's shard, same buffers)
+    def time_kernel(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    volpad = be.pad(vol)
+    import ctypes
+    from tomography_alignment_b200 import _lib
+    L = be.lib
+
+    def k_fwd():
+        _lib.check(L.tomo_forward(be._g(), ctypes.c_void_p(be.views.data_ptr()), my_n, ctypes.c_void_p(volpad.data_ptr()),
+                                  ctypes.c_void_p(proj.data_ptr()), be._stream()), "tomo_forward")
+
+    def k_back():
+        _lib.check(L.tomo_back_adjoint(be._g(), ctypes.c_void_p(be.views.data_ptr()), my_n,
+                                       ctypes.c_void_p(meas.data_ptr()), ctypes.c_void_p(bp.data_ptr()), 0, be._stream()),
+                   "tomo_back_adjoint")
+
+    def k_grad():
+        be.proj_grad(vol, meas=meas, want_proj=False, want_dproj=False, repad=False)
+
+    t_f, t_b, t_g = time_kernel(k_fwd), time_kernel(k_back), time_kernel(k_grad)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # algorithmic bytes per launch: every operator touches each fp32 voxel once per view
+    # plus detector-side traffic
+    bytes_f = my_n * (4 * n_vox + 4 * n_det)
+    bytes_b = my_n * (4 * n_vox + 4 * n_det)
+    bytes_g = my_n * (4 * n_vox + 4 * n_det) + 48 * my_n
+    kernels = {"ray_kernel<forward>": (t_f, bytes_f), "adjoint_gather_kernel": (t_b, bytes_b),
+               "ray_kernel<gradient>": (t_g, bytes_g)}
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    ach = kernels[dom][1] / (kernels[dom][0] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "per_kernel_ms": {k: v[0] for k, v in kernels.items()},
+                "per_kernel_algorithmic_gbs": {k: v[1] / (v[0] * 1e-3) / 1e9 for k, v in kernels.items()},
+                "step_frac_of_peak": (bytes_f + bytes_b + bytes_g) * world / (ms_per_step * 1e-3) / 1e9 / peak / world}
+
+    # end to end through the public API with pinned host buffers
+    e2e = None
+    if not a.no_e2e:
+        pm = ProjectionMatrix(geo, precision=np.float32, device=dev, backend=be)
+        A = pm.projection_matrix(phi=est[mine, 0], alpha=est[mine, 1], beta=est[mine, 2], xyz_shift=est[mine, 3:6])
+        h_vol = vol.cpu().pin_memory()
+        h_meas = meas.cpu().pin_memory()
+        h_proj = torch.empty((my_n * n * n,), dtype=torch.float32).pin_memory()
+        h_bp = torch.empty((n ** 3,), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            p = A @ h_vol                                            # H2D volume, forward, D2H projections
+            h_proj.copy_(p)
+            r = h_meas.reshape(-1) - h_proj                          # residual on the host, like recon/sirt.py:60
+            v = A.T @ r                                              # H2D residual, adjoint, D2H volume
+            if world > 1:
+                dist.all_reduce(v)
+            h_bp.copy_(v)
+            o = pm.projection_gradient_batch(h_vol, est[mine, 0:3], est[mine, 3:6], est[mine, 6:9], meas=h_meas,
+                                             want_dproj=False, want_proj=False)
+            g6 = o["grad6"].cpu()                                    # D2H (n, 6) gradient table
+            c = o["cost"].cpu()
+            return g6, c
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        reps = max(1, min(a.steps, 2))
+        for _ in range(reps):
+            e2e_step()
+        sync_all()
+        dt = (time.perf_counter() - t0) / reps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = 4 * (n ** 3) * 2 + 4 * my_n * n * n * 2               # vol (fwd) + residual (back) + vol, meas (grad)
+        d2h = 4 * my_n * n * n + 4 * n ** 3 + 8 * my_n * 7
+        e2e = {"value": updates_per_step / tt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": tt.item() * 1e3}
+
+    if rank == 0:
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            cpu, _ = cpu_sample(a.cpu_size)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(a), "n_vox": int(n_vox), "n_proj": n_proj,
+                           "views_per_gpu": int(my_n), "parallelism": "views sharded x%d, volume replicated" % world,
+                           "l2": "inputs exceed L2 (volume %d MiB, projections %d MiB per rank)"
+                                 % (4 * n ** 3 // 2 ** 20, 4 * my_n * n * n // 2 ** 20),
+                           "phantom": "shepp3d", "poses": "examples/generate_data.py jitter, seed 20240229"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "impl": "b200"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

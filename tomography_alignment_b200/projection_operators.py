@@ -11,8 +11,8 @@ reference's solvers use the matrix:
     A.shape
 
 numpy in -> numpy out (host<->device copies inside the call, like a scipy matvec on host arrays);
-torch CUDA tensor in -> torch CUDA tensor out (no copies; what device-resident solvers and
-bench.py's kernel timing use).  All arithmetic runs in libtomo_b200.so on the GPU; there is no CPU
+torch tensor in -> torch CUDA tensor out (no copy for a CUDA tensor, an asynchronous H2D copy for a
+(pinned) host tensor; what device-resident solvers and bench.py use).  All arithmetic runs in libtomo_b200.so on the GPU; there is no CPU
 path -- without CUDA, applying the operator raises.
 """
 import numpy as np
@@ -64,6 +64,10 @@ def pose_table(angles, xyz_shift, cor_shift):
 
 def _is_torch(x):
     return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _numel(x):
+    return x.numel() if _is_torch(x) else np.size(x)
 
 
 class ProjectionOperator(object):
@@ -123,9 +127,9 @@ class ProjectionOperator(object):
         return self._mask_dev
 
     def _matvec(self, x):
-        if np.size(x) != self._n_vox:
+        if _numel(x) != self._n_vox:
             raise ValueError("dimension mismatch: operator has %d columns, vector has %d entries"
-                             % (self._n_vox, np.size(x)))
+                             % (self._n_vox, _numel(x)))
         was_torch = _is_torch(x)
         xd = self._backend._as_vol(x if was_torch else np.ascontiguousarray(np.asarray(x), dtype=np.float32))
         if self._mask is not None:
@@ -137,9 +141,9 @@ class ProjectionOperator(object):
         return y.cpu().numpy().astype(np.result_type(self._precision, np.asarray(x).dtype), copy=False)
 
     def _rmatvec(self, y):
-        if np.size(y) != self._n_proj * self._n_det:
+        if _numel(y) != self._n_proj * self._n_det:
             raise ValueError("dimension mismatch: operator has %d rows, vector has %d entries"
-                             % (self._n_proj * self._n_det, np.size(y)))
+                             % (self._n_proj * self._n_det, _numel(y)))
         was_torch = _is_torch(y)
         yd = self._backend._as_proj(y if was_torch else np.ascontiguousarray(np.asarray(y), dtype=np.float32))
         v = self._backend.adjoint(yd).reshape(-1)
