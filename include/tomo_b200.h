@@ -93,9 +93,16 @@ TOMO_API int tomo_forward(const TomoGeom* geom, const void* views_dev, int n_pro
 
 /* vol (+)= A^T y, the exact transpose of tomo_forward: replaces
  * sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A), y) (recon/sirt.py:61, recon/cgls.py:54,72).
- * Gather formulation, no atomics, bitwise deterministic.  vol_dev is the UNPADDED volume. */
+ * Tile-owned scatter in shared memory: no atomics, bitwise deterministic.  vol_dev is the UNPADDED
+ * volume. */
 TOMO_API int tomo_back_adjoint(const TomoGeom* geom, const void* views_dev, int n_proj,
                       const float* proj_dev, float* vol_dev, int accumulate, void* stream);
+
+/* Same operator and contract as tomo_back_adjoint, computed by the per-voxel gather kernel (an
+ * independent formulation: ~8x slower, used as the cross-check of the tile-scatter kernel and for
+ * poses outside its envelope, i.e. views whose rays are nearly parallel to z). */
+TOMO_API int tomo_back_adjoint_gather(const TomoGeom* geom, const void* views_dev, int n_proj,
+                             const float* proj_dev, float* vol_dev, int accumulate, void* stream);
 
 /* vol (+)= voxel-driven bilinear backprojection, the orphan matrix-free back_project
  * (src/back_projection.f90:1-34, src/external_back_projection.f90:1-68): x' = Ry(b)(Rx(a)Rz(p)x + t),

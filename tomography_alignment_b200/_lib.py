@@ -60,6 +60,8 @@ def load():
     L.tomo_forward.argtypes = [G, vp, ci, vp, vp, vp]
     L.tomo_back_adjoint.restype = ci
     L.tomo_back_adjoint.argtypes = [G, vp, ci, vp, vp, ci, vp]
+    L.tomo_back_adjoint_gather.restype = ci
+    L.tomo_back_adjoint_gather.argtypes = [G, vp, ci, vp, vp, ci, vp]
     L.tomo_back_voxel_bilinear.restype = ci
     L.tomo_back_voxel_bilinear.argtypes = [G, vp, ci, vp, vp, vp, ci, vp]
     L.tomo_proj_grad_workspace_bytes.restype = sz

@@ -25,7 +25,9 @@ enum {
     V_RB   = 71,   // 3   candidate half-widths in lattice coords: sum_a |Linv[k][a]|
     V_VROT = 74,   // 9   row-major Ry(b) Rx(a) Rz(p)      (src/external_back_projection.f90:17-25)
     V_VTR  = 83,   // 3   Ry(b) t
-    V_END  = 86
+    V_NCOL = 86,   // 1   ray colour classes of the tile-scatter backprojector (0: not applicable)
+    V_NUNCOL = 87, // 1   RECORD 0 ONLY: number of views of this table with V_NCOL == 0
+    V_END  = 88
 };
 
 static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");
@@ -36,3 +38,9 @@ static inline
 __host__ __device__
 #endif
 int tomo_nzp(int nz) { return ((nz + 2 * TOMO_PAD + 31) / 32) * 32; }
+
+// Tile of the scatter backprojector (back_kernels.cu); the host needs the xy extent to bound the
+// z drift of a ray inside a tile when it counts colour classes.
+#define TOMO_BT_X 16
+#define TOMO_BT_Y 16
+#define TOMO_BT_Z 30

@@ -139,10 +139,36 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
             o[V_RB + k] = std::fabs(Li[k][0]) + std::fabs(Li[k][1]) + std::fabs(Li[k][2]);
         }
 
+        // Colour classes for the tile-scatter backprojector.  Rays ix and ix' are processed concurrently
+        // by different warps of a block only if ix == ix' (mod C); their samples must then never share
+        // a corner voxel.  Two samples differ by d = C k U + m D + n W (k != 0).  They can share a
+        // z-corner only while |d_z| < 2, i.e. |n| <= n_over, where inside one tile |m|,|C k| are
+        // bounded by the tile's lattice span; for those n the xy separation is at least
+        // (C perp - n_over |W_xy|) / sqrt(2) in max-norm, perp = distance between neighbouring rays'
+        // xy lines.  C is the smallest count that keeps this >= 2 (then the 2x2 corner cells differ).
+        {
+            const double dxy = std::sqrt(D.v[0] * D.v[0] + D.v[1] * D.v[1]);
+            const double wz = std::fabs(W.v[2]);
+            double ncol = 0.0;
+            if (dxy > 1e-6 && wz >= 0.6) {
+                const double perp = std::fabs(U.v[0] * D.v[1] - U.v[1] * D.v[0]) / dxy;
+                const double wxy = std::sqrt(W.v[0] * W.v[0] + W.v[1] * W.v[1]);
+                const double span = 2.0 * (TOMO_BT_X + TOMO_BT_Y + 8);
+                const double zdrift = span * (std::fabs(U.v[2]) + std::fabs(D.v[2]));
+                const double n_over = std::ceil((2.0 + zdrift) / wz) - 1.0;
+                for (int C = 1; C <= 16; ++C)
+                    if ((C * perp - n_over * wxy) / std::sqrt(2.0) >= 2.02) { ncol = C; break; }
+            }
+            o[V_NCOL] = ncol;
+        }
+
         // voxel-driven (inverse convention) transform  Ry (Rx Rz x + t)   (external_back_projection.f90:17-25)
         const M3 Vr = mul(Rb, mul(Ra, Rp));
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[V_VROT + 3 * i + j] = Vr.m[i][j];
         put(o + V_VTR, mul(Rb, t));
     }
+    double n_uncoloured = 0.0;
+    for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_NCOL] == 0.0) n_uncoloured += 1.0;
+    out[V_NUNCOL] = n_uncoloured;
     return 0;
 }

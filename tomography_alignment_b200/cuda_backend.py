@@ -100,15 +100,16 @@ class CudaBackend(object):
         self.launches += 1
         return out
 
-    def adjoint(self, y, out=None, accumulate=False):
-        """vol (+)= A^T y: float32 (nx, ny, nz) on the device."""
+    def adjoint(self, y, out=None, accumulate=False, gather=False):
+        """vol (+)= A^T y: float32 (nx, ny, nz) on the device.  ``gather=True`` uses the per-voxel gather
+        kernel (tomo_back_adjoint_gather), the independent formulation kept as a cross-check."""
         y = self._as_proj(y)
         if out is None:
             out = torch.empty(self.vol_shape, dtype=torch.float32, device=self.device)
             accumulate = False
+        fn = self.lib.tomo_back_adjoint_gather if gather else self.lib.tomo_back_adjoint
         with torch.cuda.device(self.device):
-            rc = self.lib.tomo_back_adjoint(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out),
-                                            int(bool(accumulate)), self._stream())
+            rc = fn(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out), int(bool(accumulate)), self._stream())
         _lib.check(rc, "tomo_back_adjoint")
         self.launches += 1
         return out
