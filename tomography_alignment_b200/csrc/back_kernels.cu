@@ -87,150 +87,195 @@ voxel_bilinear_kernel(const BackArgs A)
 
 
 constexpr int TNW = 8;     // warps per block of the tile kernel
+constexpr int TSX = TOMO_BT_X + 4, TSY = TOMO_BT_Y + 4, TSZ = TOMO_BT_Z + 4;   // smem tile incl. 2 ghost cells per side
 
-template <int TX, int TY>
+// Per-view constants of the tile kernel, float32 and tile-local: p_s = Bc + di*U + dk*W + dj*D with
+// di = ix - ix_lo, dk = iz - iz_lo, dj = j - jc (all small), p_s in smem-cell coordinates.
+struct TileView {
+    float Bc[3], U[3], W[3], D[3], invD[3];
+    float df[3];            // fractional part of |D|
+    int   di_step;          // integer part of |D| folded into the address step (mirrored frame)
+    int   zi_step;
+    int   ix_lo, ix_hi, iz_lo, iz_hi, jc, djmin, djmax, ncol;
+    float dupthr;           // same-z-cell test threshold for adjacent lanes
+};
+
+// March the rays of one view through the tile.  SGX/SGY/SGZ = sign of D per axis: with the mirrored
+// frame q = SG * p_s the carries are one-sided and the 7 corner offsets are compile-time immediates.
+template <int SGX, int SGY, int SGZ>
+__device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const TileView& tv,
+                                                const float* __restrict__ P, int ndz, int lane, int warp)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int STX = SGX * TSY * TSZ, STY = SGY * TSZ, STZ = SGZ;
+    constexpr int O01 = STY, O10 = STX, O11 = STX + STY, OZ = STZ;
+    const float hi[3] = {(float)(TOMO_BT_X + 2), (float)(TOMO_BT_Y + 2), (float)(TOMO_BT_Z + 2)};
+    const int stepoff = tv.di_step;
+    for (int c = 0; c < tv.ncol; ++c) {
+        const int first = tv.ix_lo + (((c - tv.ix_lo) % tv.ncol) + tv.ncol) % tv.ncol;
+        for (int ix = first + tv.ncol * warp; ix <= tv.ix_hi; ix += tv.ncol * TNW) {
+            for (int izb = tv.iz_lo; izb <= tv.iz_hi; izb += 32) {
+                const int iz = izb + lane;
+                const bool valid = iz <= tv.iz_hi;
+                const float fdi = (float)(ix - tv.ix_lo), fdk = (float)(iz - tv.iz_lo);
+                float pr[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) pr[a] = fmaf(fdk, tv.W[a], fmaf(fdi, tv.U[a], tv.Bc[a]));
+                // per-lane sample range (relative to jc) inside the tile's active box 1 <= p_s < T+2
+                float jlo = (float)tv.djmin, jhi = (float)tv.djmax;
+                bool empty = !valid;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (tv.D[a] > 0.f)      { jlo = fmaxf(jlo, (1.f - pr[a]) * tv.invD[a]);   jhi = fminf(jhi, (hi[a] - pr[a]) * tv.invD[a]); }
+                    else if (tv.D[a] < 0.f) { jlo = fmaxf(jlo, (hi[a] - pr[a]) * tv.invD[a]); jhi = fminf(jhi, (1.f - pr[a]) * tv.invD[a]); }
+                    else if (pr[a] < 1.f || pr[a] >= hi[a]) empty = true;
+                }
+                jlo = fminf(fmaxf(jlo, -1.0e6f), 1.0e6f);
+                jhi = fminf(fmaxf(jhi, -1.0e6f), 1.0e6f);
+                int j0 = (int)ceilf(jlo), j1 = min((int)floorf(jhi) + 1, tv.djmax);
+                if (empty || j1 <= j0) { j0 = 0x7fffffff; j1 = -0x7fffffff; }
+                const int jw0 = __reduce_min_sync(FULL, j0), jw1 = __reduce_max_sync(FULL, j1);
+                if (jw0 >= jw1) continue;                                   // warp-uniform
+                const bool live = j1 > j0;
+                const float yv = live ? __ldg(P + (size_t)ix * ndz + iz) : 0.f;
+                const unsigned span = live ? (unsigned)(j1 - j0) : 0u;
+                unsigned k = (unsigned)(jw0 - (live ? j0 : 0));             // j - j0, wraps below zero
+
+                // mirrored-frame state at sample jw0
+                const float fj = (float)jw0;
+                const float qx = (float)SGX * fmaf(fj, tv.D[0], pr[0]);
+                const float qy = (float)SGY * fmaf(fj, tv.D[1], pr[1]);
+                const float qz = (float)SGZ * fmaf(fj, tv.D[2], pr[2]);
+                const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
+                float f0 = qx - flx, f1 = qy - fly, f2 = qz - flz;
+                int off = (int)flx * STX + (int)fly * STY + (int)flz * STZ;
+                float* __restrict__ s = acc + off;
+                for (int j = jw0; j < jw1; ++j) {
+                    const bool act = k < span;
+                    // lane l+1 sits in lane l's z cell iff its own fraction says so (no shuffle needed):
+                    // mirrored z decreases (SGZ < 0) or increases (SGZ > 0) by W_z per lane
+                    const bool dup = act && ((SGZ > 0) ? (f2 >= tv.dupthr) : (f2 < 1.f - tv.dupthr));
+                    const float wx1 = f0 * yv, wx0 = yv - wx1;
+                    const float wy0 = 1.f - f1, wz0 = 1.f - f2;
+                    const float w00 = wx0 * wy0, w01 = wx0 * f1, w10 = wx1 * wy0, w11 = wx1 * f1;
+                    if (!__any_sync(FULL, dup)) {
+                        if (act) {
+                            const float a0 = s[0], a1 = s[O01], a2 = s[O10], a3 = s[O11];
+                            s[0] = fmaf(w00, wz0, a0); s[O01] = fmaf(w01, wz0, a1);
+                            s[O10] = fmaf(w10, wz0, a2); s[O11] = fmaf(w11, wz0, a3);
+                        }
+                        __syncwarp();
+                        if (act) {
+                            const float a0 = s[OZ], a1 = s[OZ + O01], a2 = s[OZ + O10], a3 = s[OZ + O11];
+                            s[OZ] = fmaf(w00, f2, a0); s[OZ + O01] = fmaf(w01, f2, a1);
+                            s[OZ + O10] = fmaf(w10, f2, a2); s[OZ + O11] = fmaf(w11, f2, a3);
+                        }
+                        __syncwarp();
+                    } else {
+                        // rare (W_z < 1 makes two adjacent lanes share a z cell ~ once per 1/(1-W_z) samples):
+                        // lanes flagged dup go in a second pass
+#pragma unroll 1
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const bool go = act && (dup == (pass == 1));
+                            if (go) {
+                                const float a0 = s[0], a1 = s[O01], a2 = s[O10], a3 = s[O11];
+                                s[0] = fmaf(w00, wz0, a0); s[O01] = fmaf(w01, wz0, a1);
+                                s[O10] = fmaf(w10, wz0, a2); s[O11] = fmaf(w11, wz0, a3);
+                            }
+                            __syncwarp();
+                            if (go) {
+                                const float a0 = s[OZ], a1 = s[OZ + O01], a2 = s[OZ + O10], a3 = s[OZ + O11];
+                                s[OZ] = fmaf(w00, f2, a0); s[OZ + O01] = fmaf(w01, f2, a1);
+                                s[OZ + O10] = fmaf(w10, f2, a2); s[OZ + O11] = fmaf(w11, f2, a3);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    // advance one sample: one-sided carries, immediate strides
+                    ++k;
+                    f0 += tv.df[0]; f1 += tv.df[1]; f2 += tv.df[2];
+                    s += stepoff;
+                    if (f0 >= 1.0f) { f0 -= 1.0f; s += STX; }
+                    if (f1 >= 1.0f) { f1 -= 1.0f; s += STY; }
+                    if (f2 >= 1.0f) { f2 -= 1.0f; s += STZ; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(TNW * 32)
 adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int ntz)
 {
-    constexpr int TZ = TOMO_BT_Z, SX = TX + 4, SY = TY + 4, SZ = TZ + 4;
-    constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ float acc[];                       // [SX][SY][SZ], 2 ghost cells per side
+    constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
+    extern __shared__ float acc[];                       // [TSX][TSY][TSZ]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int bb = blockIdx.x;
     const int tz = bb % ntz; bb /= ntz;
     const int ty = bb % nty;
     const int tx = bb / nty;
-    const int org[3] = {tx * TX - 2, ty * TY - 2, tz * TZ - 2};   // voxel coordinate of smem index 0
-    for (int i = threadIdx.x; i < SX * SY * SZ; i += TNW * 32) acc[i] = 0.f;
+    const int org[3] = {tx * TX - 2, ty * TY - 2, tz * TZ - 2};   // voxel coordinate of smem cell 0
+    for (int i = threadIdx.x; i < TSX * TSY * TSZ; i += TNW * 32) acc[i] = 0.f;
     __syncthreads();
 
     const size_t n_det = (size_t)A.ndx * A.ndz;
-    const int ust[3] = {SY * SZ, SZ, 1};
     // a sample is ours iff its floor cell lies in [1, T+1] per axis, i.e. 1 <= p_s < T+2 (smem coordinates)
-    const float hi[3] = {(float)(TX + 2), (float)(TY + 2), (float)(TZ + 2)};
-    const double hw[3] = {0.5 * (TX + 1) + 1e-3, 0.5 * (TY + 1) + 1e-3, 0.5 * (TZ + 1) + 1e-3};
+    const double hw[3] = {0.5 * (TX + 1), 0.5 * (TY + 1), 0.5 * (TZ + 1)};
 
     for (int view = 0; view < A.n_proj; ++view) {
         const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
-        const float* __restrict__ P = A.proj + (size_t)view * n_det;
-        const int ncol = (int)V[V_NCOL];
-        const int nsamp = (int)V[V_N];
-        if (ncol == 0) continue;                         // outside the scatter envelope: the gather kernel adds it
-        // lattice bounding box of the active region: centre +- sum |Linv| * half widths
+        TileView tv;
+        tv.ncol = (int)V[V_NCOL];
+        if (tv.ncol == 0) continue;                      // outside the scatter envelope: the gather kernel adds it
+        // lattice coordinates of the active box: centre +- sum |Linv| * half widths (exact for a linear map)
         double B[3], cc[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             B[a] = V[V_P00 + a] - (double)org[a];        // p_s = B + ix U + iz W + j D
-            cc[a] = 1.0 + hw[a] - 1e-3 - B[a];           // box centre minus lattice origin
+            cc[a] = 1.0 + hw[a] - B[a];
         }
-        const double ixc = V[V_LINV + 0] * cc[0] + V[V_LINV + 1] * cc[1] + V[V_LINV + 2] * cc[2];
-        const double izc = V[V_LINV + 3] * cc[0] + V[V_LINV + 4] * cc[1] + V[V_LINV + 5] * cc[2];
-        const double rix = fabs(V[V_LINV + 0]) * hw[0] + fabs(V[V_LINV + 1]) * hw[1] + fabs(V[V_LINV + 2]) * hw[2];
-        const double riz = fabs(V[V_LINV + 3]) * hw[0] + fabs(V[V_LINV + 4]) * hw[1] + fabs(V[V_LINV + 5]) * hw[2];
-        const int ix_lo = max(0, (int)ceil(fmax(ixc - rix, -1.0))), ix_hi = min(A.ndx - 1, (int)floor(fmin(ixc + rix, 2.0e9)));
-        const int iz_lo = max(0, (int)ceil(fmax(izc - riz, -1.0))), iz_hi = min(A.ndz - 1, (int)floor(fmin(izc + riz, 2.0e9)));
-        if (ix_lo > ix_hi || iz_lo > iz_hi) continue;    // block-uniform: no ray of this view crosses the tile
-
-        // mirrored-frame constants (as in ray_core.h): one-sided carries, signed smem strides
-        float df[3], invd[3], dD[3];
-        int sg[3], st[3], stepoff = 0, zstep;
+        double lc[3], lr[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lc[k] = V[V_LINV + 3 * k] * cc[0] + V[V_LINV + 3 * k + 1] * cc[1] + V[V_LINV + 3 * k + 2] * cc[2];
+            lr[k] = fabs(V[V_LINV + 3 * k]) * hw[0] + fabs(V[V_LINV + 3 * k + 1]) * hw[1] + fabs(V[V_LINV + 3 * k + 2]) * hw[2] + 1e-3;
+        }
+        tv.ix_lo = max(0, (int)ceil(fmax(lc[0] - lr[0], -1.0)));
+        tv.ix_hi = min(A.ndx - 1, (int)floor(fmin(lc[0] + lr[0], 2.0e9)));
+        tv.iz_lo = max(0, (int)ceil(fmax(lc[1] - lr[1], -1.0)));
+        tv.iz_hi = min(A.ndz - 1, (int)floor(fmin(lc[1] + lr[1], 2.0e9)));
+        const int nsamp = (int)V[V_N];
+        const int j_lo = max(0, (int)ceil(fmax(lc[2] - lr[2], -1.0))), j_hi = min(nsamp - 1, (int)floor(fmin(lc[2] + lr[2], 2.0e9)));
+        if (tv.ix_lo > tv.ix_hi || tv.iz_lo > tv.iz_hi || j_lo > j_hi) continue;   // block-uniform: nothing of this view crosses the tile
+        tv.jc = (j_lo + j_hi) / 2;
+        tv.djmin = j_lo - tv.jc;
+        tv.djmax = j_hi - tv.jc + 1;
+        int sx = 1, sy = 1, sz = 1;
+        tv.di_step = 0; tv.zi_step = 0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const double d = V[V_D + a], ad = fabs(d), ai = floor(ad);
-            dD[a] = (float)d;
-            invd[a] = (float)V[V_INVD + a];
-            df[a] = (float)(ad - ai);
-            sg[a] = (d < 0.0) ? -1 : 1;
-            st[a] = sg[a] * ust[a];
-            stepoff += (int)ai * st[a];
-            if (a == 2) zstep = (int)ai * sg[a];
+            tv.Bc[a] = (float)(B[a] + (double)tv.ix_lo * V[V_U + a] + (double)tv.iz_lo * V[V_W + a] + (double)tv.jc * d);
+            tv.U[a] = (float)V[V_U + a]; tv.W[a] = (float)V[V_W + a]; tv.D[a] = (float)d;
+            tv.invD[a] = (float)V[V_INVD + a];
+            tv.df[a] = (float)(ad - ai);
+            const int sg = (d < 0.0) ? -1 : 1;
+            if (a == 0) sx = sg; else if (a == 1) sy = sg; else sz = sg;
+            tv.di_step += (int)ai * sg * ((a == 0) ? TSY * TSZ : (a == 1) ? TSZ : 1);
         }
-        const int o01 = st[1], o10 = st[0], o11 = st[0] + st[1], oz = st[2];
-
-        for (int c = 0; c < ncol; ++c) {
-            const int first = ix_lo + (((c - ix_lo) % ncol) + ncol) % ncol;
-            for (int ix = first + ncol * warp; ix <= ix_hi; ix += ncol * TNW) {
-                for (int izb = iz_lo; izb <= iz_hi; izb += 32) {
-                    const int iz = izb + lane;
-                    const bool valid = iz <= iz_hi;
-                    double pr[3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) pr[a] = B[a] + (double)ix * V[V_U + a] + (double)iz * V[V_W + a];
-                    // per-lane sample range inside the tile's active box
-                    float jlo = 0.f, jhi = (float)nsamp;
-                    bool empty = !valid;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const float p = (float)pr[a];
-                        if (dD[a] > 0.f)      { jlo = fmaxf(jlo, (1.f - p) * invd[a]);   jhi = fminf(jhi, (hi[a] - p) * invd[a]); }
-                        else if (dD[a] < 0.f) { jlo = fmaxf(jlo, (hi[a] - p) * invd[a]); jhi = fminf(jhi, (1.f - p) * invd[a]); }
-                        else if (p < 1.f || p >= hi[a]) empty = true;
-                    }
-                    jlo = fminf(fmaxf(jlo, 0.f), (float)nsamp);
-                    jhi = fminf(fmaxf(jhi, -1.f), (float)nsamp);
-                    int j0 = (int)ceilf(jlo), j1 = min((int)floorf(jhi) + 1, nsamp);
-                    if (empty || j1 <= j0) { j0 = 0x7fffffff; j1 = -0x7fffffff; }
-                    const int jw0 = __reduce_min_sync(FULL, j0), jw1 = __reduce_max_sync(FULL, j1);
-                    if (jw0 >= jw1) continue;                                   // warp-uniform
-                    const float yv = (j1 > j0) ? __ldg(P + (size_t)ix * A.ndz + iz) : 0.f;
-
-                    // state at sample jw0, from float64
-                    float f[3];
-                    int off = 0, zc = 0;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const double q = (double)sg[a] * (pr[a] + (double)jw0 * V[V_D + a]);
-                        const double qi = floor(q);
-                        f[a] = (float)(q - qi);
-                        int i = (int)fmin(fmax(qi, -1.0e6), 1.0e6);
-                        if (f[a] >= 1.0f) { f[a] -= 1.0f; i += 1; }
-                        off += sg[a] * i * ust[a];
-                        if (a == 2) zc = sg[a] * i;
-                    }
-                    for (int j = jw0; j < jw1; ++j) {
-                        const bool act = (j >= j0) && (j < j1);
-                        // adjacent lanes in the same z cell would alias inside one instruction
-                        const int zprev = __shfl_up_sync(FULL, zc, 1);
-                        const bool aprev = __shfl_up_sync(FULL, (int)act, 1) != 0;
-                        const bool dup = act && aprev && (lane > 0) && (zprev == zc);
-                        const bool anydup = __any_sync(FULL, dup);
-                        const float wx1 = f[0] * yv, wx0 = yv - wx1;
-                        const float wy1 = f[1], wy0 = 1.f - wy1;
-                        const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
-                        const float wz1 = f[2], wz0 = 1.f - wz1;
-                        float* __restrict__ s = acc + off;
-                        bool go = act && !dup;
-#pragma unroll 1
-                        for (int pass = 0; pass < 2; ++pass) {
-                            if (go) {
-                                const float a0 = s[0], a1 = s[o01], a2 = s[o10], a3 = s[o11];
-                                s[0]   = fmaf(w00, wz0, a0);
-                                s[o01] = fmaf(w01, wz0, a1);
-                                s[o10] = fmaf(w10, wz0, a2);
-                                s[o11] = fmaf(w11, wz0, a3);
-                            }
-                            __syncwarp();
-                            if (go) {
-                                const float a0 = s[oz], a1 = s[oz + o01], a2 = s[oz + o10], a3 = s[oz + o11];
-                                s[oz]       = fmaf(w00, wz1, a0);
-                                s[oz + o01] = fmaf(w01, wz1, a1);
-                                s[oz + o10] = fmaf(w10, wz1, a2);
-                                s[oz + o11] = fmaf(w11, wz1, a3);
-                            }
-                            __syncwarp();
-                            if (!anydup) break;
-                            go = dup;
-                        }
-                        // advance one sample
-                        f[0] += df[0]; f[1] += df[1]; f[2] += df[2];
-                        off += stepoff; zc += zstep;
-                        if (f[0] >= 1.0f) { f[0] -= 1.0f; off += st[0]; }
-                        if (f[1] >= 1.0f) { f[1] -= 1.0f; off += st[1]; }
-                        if (f[2] >= 1.0f) { f[2] -= 1.0f; off += st[2]; zc += sg[2]; }
-                    }
-                }
-            }
-            __syncthreads();
+        // adjacent lanes share a z cell iff frac >= W_z (mirrored: frac < 1 - W_z); margin for float32 marching
+        tv.dupthr = (float)fabs(V[V_W + 2]) - 2e-4f;
+        const float* __restrict__ P = A.proj + (size_t)view * n_det;
+        switch ((sx < 0 ? 4 : 0) | (sy < 0 ? 2 : 0) | (sz < 0 ? 1 : 0)) {       // block-uniform
+            case 0: tile_march_view< 1,  1,  1>(acc, tv, P, A.ndz, lane, warp); break;
+            case 1: tile_march_view< 1,  1, -1>(acc, tv, P, A.ndz, lane, warp); break;
+            case 2: tile_march_view< 1, -1,  1>(acc, tv, P, A.ndz, lane, warp); break;
+            case 3: tile_march_view< 1, -1, -1>(acc, tv, P, A.ndz, lane, warp); break;
+            case 4: tile_march_view<-1,  1,  1>(acc, tv, P, A.ndz, lane, warp); break;
+            case 5: tile_march_view<-1,  1, -1>(acc, tv, P, A.ndz, lane, warp); break;
+            case 6: tile_march_view<-1, -1,  1>(acc, tv, P, A.ndz, lane, warp); break;
+            default: tile_march_view<-1, -1, -1>(acc, tv, P, A.ndz, lane, warp); break;
         }
     }
     __syncthreads();
@@ -239,7 +284,7 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
         const int zz = i & 31, yy = (i >> 5) % TY, xx = (i >> 5) / TY;
         const int x = tx * TX + xx, y = ty * TY + yy, z = tz * TZ + zz;
         if (zz < TZ && x < A.nx && y < A.ny && z < A.nz) {
-            const float v = acc[((xx + 2) * SY + (yy + 2)) * SZ + zz + 2];
+            const float v = acc[((xx + 2) * TSY + (yy + 2)) * TSZ + zz + 2];
             const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
             A.vol[vi] = A.accumulate ? A.vol[vi] + v : v;
         }
@@ -283,9 +328,9 @@ extern "C" int tomo_back_adjoint(const TomoGeom* g, const void* views, int n_pro
     const size_t smem = sizeof(float) * (TX + 4) * (TY + 4) * (TZ + 4);
     const double nblocks = (double)ntx * nty * ntz;
     if (nblocks >= 2147483647.0) { tomo_set_error("tomo_back_adjoint: too many tiles"); return TOMO_E_RANGE; }
-    cudaError_t ce = cudaFuncSetAttribute(adjoint_tile_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = cudaFuncSetAttribute(adjoint_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (int e = tomo_check_cuda(ce, "cudaFuncSetAttribute(adjoint_tile_kernel)")) return e;
-    adjoint_tile_kernel<TX, TY><<<(unsigned)(ntx * nty * ntz), TNW * 32, smem, (cudaStream_t)stream>>>(A, ntx, nty, ntz);
+    adjoint_tile_kernel<<<(unsigned)(ntx * nty * ntz), TNW * 32, smem, (cudaStream_t)stream>>>(A, ntx, nty, ntz);
     if (int e = tomo_check_cuda(cudaGetLastError(), "adjoint_tile_kernel")) return e;
     // views outside the scatter envelope (rays nearly parallel to z; none for tomographic poses): the
     // gather kernel adds them; it returns at once when record 0 says there are none

@@ -148,7 +148,7 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
         // xy lines.  C is the smallest count that keeps this >= 2 (then the 2x2 corner cells differ).
         {
             const double dxy = std::sqrt(D.v[0] * D.v[0] + D.v[1] * D.v[1]);
-            const double wz = std::fabs(W.v[2]);
+            const double wz = W.v[2];        // lanes must advance towards +z (positive detector pitch)
             double ncol = 0.0;
             if (dxy > 1e-6 && wz >= 0.6) {
                 const double perp = std::fabs(U.v[0] * D.v[1] - U.v[1] * D.v[0]) / dxy;
