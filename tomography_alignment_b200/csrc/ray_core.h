@@ -138,6 +138,7 @@ TOMO_HD float fix_to_float(unsigned hi)
 // Forward only: (cell offset, float32 fraction) marching, re-based from float64 every RAY_REBASE
 // samples.  The interpolant is continuous, so a cell decision that is off by float32 rounding next
 // to a lattice plane changes nothing.
+template <int SGZ>
 TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
                                int ix, int iz, RaySums& out)
 {
@@ -147,7 +148,9 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
     float df[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) { const double ad = fabs(r.D[a]); df[a] = (float)(ad - floor(ad)); }
-    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1], oz = r.st[2];
+    // the z stride (+-1) is a template constant: the z-ceil corner of each pair is an immediate offset
+    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1];
+    constexpr int oz = SGZ;
     float acc = 0.f;
     for (int jc = r.j0; jc < r.j1; jc += RAY_REBASE) {
         float f[3];
@@ -168,7 +171,7 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
             off += r.stepoff;
             if (f[0] >= 1.0f) { f[0] -= 1.0f; off += r.st[0]; }
             if (f[1] >= 1.0f) { f[1] -= 1.0f; off += r.st[1]; }
-            if (f[2] >= 1.0f) { f[2] -= 1.0f; off += r.st[2]; }
+            if (f[2] >= 1.0f) { f[2] -= 1.0f; off += SGZ; }
         }
     }
     out.acc = acc;
@@ -178,13 +181,15 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
 // lattice planes (one-sided differences, src/ray_wt_grad.f90:142-220), so the cell of every sample
 // must be the float64 one: the fraction is carried as 64-bit fixed point, which accumulates j*D
 // exactly (no re-basing, no branches); only the interpolation weights are rounded to float32.
+template <int SGZ>
 TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
                                 int ix, int iz, RaySums& out)
 {
     RaySetup r;
     ray_setup(V, dm, ix, iz, r);
     const int ust[3] = {dm.sxp, dm.syp, 1};
-    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1], oz = r.st[2];
+    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1];
+    constexpr int oz = SGZ;
     unsigned fh[3], fl[3], dh[3], dl[3];
     int off = 0;
 #pragma unroll
@@ -213,7 +218,7 @@ TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __r
         off += r.stepoff;
         off += (int)fix64_add(fh[0], fl[0], dh[0], dl[0]) * r.st[0];
         off += (int)fix64_add(fh[1], fl[1], dh[1], dl[1]) * r.st[1];
-        off += (int)fix64_add(fh[2], fl[2], dh[2], dl[2]) * r.st[2];
+        off += (int)fix64_add(fh[2], fl[2], dh[2], dl[2]) * SGZ;
     }
     out.acc = acc;
     out.s0[0] = s0x * (float)r.sg[0]; out.s0[1] = s0y * (float)r.sg[1]; out.s0[2] = s0z * (float)r.sg[2];
@@ -224,8 +229,10 @@ template <bool GRAD>
 TOMO_HD void ray_march(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
                        int ix, int iz, RaySums& out)
 {
-    if (GRAD) ray_march_gradient(vol, V, dm, ix, iz, out);
-    else      ray_march_forward(vol, V, dm, ix, iz, out);
+    // sign of the z step: uniform per view, so this branch never diverges
+    const bool zneg = V[V_D + 2] < 0.0;
+    if (GRAD) { if (zneg) ray_march_gradient<-1>(vol, V, dm, ix, iz, out); else ray_march_gradient<1>(vol, V, dm, ix, iz, out); }
+    else      { if (zneg) ray_march_forward<-1>(vol, V, dm, ix, iz, out);  else ray_march_forward<1>(vol, V, dm, ix, iz, out); }
 }
 
 // d proj / d theta_k for one ray, API order [tx, ty, tz, phi, alpha, beta]
