@@ -36,6 +36,15 @@ METRIC = "voxel-ray updates/s fwd+back+grad"
 UNIT = "voxel-ray updates/s"
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress to stderr (stdout carries only the JSON line)."""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +168,8 @@ class ClockSampler(object):
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
 def run_b200(a):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from tomography_alignment_b200 import Geometry, ProjectionMatrix, pose_table
@@ -166,6 +177,7 @@ def run_b200(a):
     from tomography_alignment_b200.phantom import benchmark_poses, shepp3d
     from tomography_alignment_b200.sharding import shard_views
 
+    log("torch imported")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -199,6 +211,7 @@ def run_b200(a):
     idx = torch.as_tensor(mine, device=dev, dtype=torch.long)
     del be_true
     torch.cuda.synchronize()
+    log("inputs ready (phantom, measured projections)")
 
     n_vox, n_det = float(n) ** 3, float(n) ** 2
     updates_per_step = 3.0 * n_vox * n_proj
@@ -226,6 +239,7 @@ def run_b200(a):
     for _ in range(a.warmup):
         step()
     sync_all()
+    log("warm-up done")
     launches0 = be.launches
     sampler = ClockSampler(local)
     if rank == 0:
@@ -274,7 +288,9 @@ def run_b200(a):
     def k_grad():
         be.proj_grad(vol, meas=meas, want_proj=False, want_dproj=False, repad=False)
 
+    log("timed steps done: %.1f ms/step" % ms_per_step)
     t_f, t_b, t_g = time_kernel(k_fwd), time_kernel(k_back), time_kernel(k_grad)
+    log("per-kernel timing done")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -302,21 +318,21 @@ def run_b200(a):
         A = pm.projection_matrix(phi=est[mine, 0], alpha=est[mine, 1], beta=est[mine, 2], xyz_shift=est[mine, 3:6])
         h_vol = vol.cpu().pin_memory()
         h_meas = meas.cpu().pin_memory()
-        h_proj = torch.empty((my_n * n * n,), dtype=torch.float32).pin_memory()
-        h_bp = torch.empty((n ** 3,), dtype=torch.float32).pin_memory()
+        h_proj = torch.empty((my_n, n, n), dtype=torch.float32).pin_memory()
+        h_bp = torch.empty((n, n, n), dtype=torch.float32).pin_memory()
+        log("pinned host buffers ready")
+
+        h_g6 = None
 
         def e2e_step():
-            p = A @ h_vol                                            # H2D volume, forward, D2H projections
-            h_proj.copy_(p)
-            r = h_meas.reshape(-1) - h_proj                          # residual on the host, like recon/sirt.py:60
-            v = A.T @ r                                              # H2D residual, adjoint, D2H volume
-            if world > 1:
+            # host buffers in, host buffers out; copies are issued inside the calls (view chunks, side stream)
+            A._backend.forward_host(h_vol, out_host=h_proj)          # H2D volume, forward, D2H projections
+            A._backend.adjoint_host(h_meas, out_host=h_bp)           # H2D projections, adjoint, D2H volume
+            if world > 1:                                            # Allreduce of recon/sirt_mpi.py:103 on host data
+                v = h_bp.to(dev, non_blocking=True)
                 dist.all_reduce(v)
-            h_bp.copy_(v)
-            o = pm.projection_gradient_batch(h_vol, est[mine, 0:3], est[mine, 3:6], est[mine, 6:9], meas=h_meas,
-                                             want_dproj=False, want_proj=False)
-            g6 = o["grad6"].cpu()                                    # D2H (n, 6) gradient table
-            c = o["cost"].cpu()
+                h_bp.copy_(v)
+            g6, c = A._backend.proj_grad_host(h_vol, h_meas)         # H2D volume + measured, D2H (n, 6) gradients
             return g6, c
 
         e2e_step()
@@ -330,8 +346,11 @@ def run_b200(a):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        h2d = 4 * (n ** 3) * 2 + 4 * my_n * n * n * 2               # vol (fwd) + residual (back) + vol, meas (grad)
-        d2h = 4 * my_n * n * n + 4 * n ** 3 + 8 * my_n * 7
+        be.h2d_bytes = be.d2h_bytes = 0
+        e2e_step()                                                   # untimed: counts the bytes one step moves
+        sync_all()
+        h2d, d2h = be.h2d_bytes, be.d2h_bytes
+        log("e2e done")
         e2e = {"value": updates_per_step / tt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": tt.item() * 1e3}
 
@@ -339,6 +358,7 @@ def run_b200(a):
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             cpu, _ = cpu_sample(a.cpu_size)
+            log("cpu baseline done")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

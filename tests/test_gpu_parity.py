@@ -244,6 +244,31 @@ def test_drop_in_operator_on_gpu_matches_reference_csr():
     assert rel_l2(proj, p) <= TOL_PROJ and rel_l2(grad, gr) <= TOL_GRAD
 
 
+def test_host_buffer_entry_points_match_device_path():
+    """forward_host / adjoint_host / proj_grad_host (copies overlapped with the kernels in view chunks, sub-tables
+    of the view table) against the device-resident calls; also through the numpy path of the operator."""
+    g, og, be, op, (phi, alpha, beta, xyz) = setup((40, 36, 44), (40, 44), 11, seed=21)
+    rng = np.random.default_rng(22)
+    vol = rng.random((40, 36, 44)).astype(np.float32)
+    y = rng.random((11, 40, 44)).astype(np.float32)
+    f_dev = be.forward(torch.as_tensor(vol)).cpu()
+    b_dev = be.adjoint(torch.as_tensor(y)).cpu()
+    g_dev = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(y), want_dproj=False)
+    for chunk in (None, 3, 11, 50):
+        f_h = be.forward_host(torch.as_tensor(vol).pin_memory(), chunk_views=chunk)
+        assert f_h.device.type == "cpu" and torch.equal(f_h.reshape(f_dev.shape), f_dev)
+        b_h = be.adjoint_host(y, chunk_views=chunk)
+        assert rel_l2(b_h.numpy(), b_dev.numpy()) < 1e-6
+        g6, c = be.proj_grad_host(vol, y, chunk_views=chunk)
+        assert torch.equal(g6, g_dev["grad6"].cpu()) and torch.equal(c, g_dev["cost"].cpu())
+    assert rel_l2(b_h.numpy(), op.adjoint(y.reshape(11, -1))) <= TOL_PROJ
+    pm = ProjectionMatrix(g, device="cuda:0", backend=be)
+    A = pm.projection_matrix(alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    ax = A @ vol.ravel()
+    assert isinstance(ax, np.ndarray) and np.array_equal(ax, f_dev.numpy().ravel())
+    assert rel_l2(A.T @ y.ravel(), b_dev.numpy()) < 1e-6
+
+
 def test_error_codes_surface_as_exceptions():
     from tomography_alignment_b200 import _lib
     g, _ = make_geoms((8, 8, 8), (8, 8), 2)

@@ -57,7 +57,7 @@ adjoint_gather_kernel(const BackArgs A)
     const int x = blockIdx.z * BX + threadIdx.z;
     if (x >= A.nx || y >= A.ny || z >= A.nz) return;
     const size_t n_det = (size_t)A.ndx * A.ndz;
-    if (A.only_uncoloured && A.views[V_NUNCOL] == 0.0) return;      // record 0 holds the count
+    if (A.only_uncoloured && A.views[V_NUNCOL] == 0.0) return;      // every record holds the table's count
     float acc = 0.f;
     for (int view = 0; view < A.n_proj; ++view) {
         const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;

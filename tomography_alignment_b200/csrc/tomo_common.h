@@ -26,7 +26,8 @@ enum {
     V_VROT = 74,   // 9   row-major Ry(b) Rx(a) Rz(p)      (src/external_back_projection.f90:17-25)
     V_VTR  = 83,   // 3   Ry(b) t
     V_NCOL = 86,   // 1   ray colour classes of the tile-scatter backprojector (0: not applicable)
-    V_NUNCOL = 87, // 1   RECORD 0 ONLY: number of views of this table with V_NCOL == 0
+    V_NUNCOL = 87, // 1   number of views of the whole table with V_NCOL == 0 (same in every record, so a
+                   //     pointer to any record is a valid sub-table)
     V_END  = 88
 };
 

@@ -169,6 +169,6 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
     }
     double n_uncoloured = 0.0;
     for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_NCOL] == 0.0) n_uncoloured += 1.0;
-    out[V_NUNCOL] = n_uncoloured;
+    for (int v = 0; v < n_proj; ++v) out[(size_t)v * TOMO_VIEW_STRIDE + V_NUNCOL] = n_uncoloured;
     return 0;
 }

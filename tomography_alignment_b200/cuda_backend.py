@@ -37,6 +37,10 @@ class CudaBackend(object):
         self._volpad = None
         self._ws = None
         self.launches = 0        # kernels of ours launched so far (bench.py reports the count)
+        self._copy = None        # side stream for host<->device copies overlapped with the kernels
+        self._dbuf = {}          # cached device staging buffers of the host-buffer entry points
+        self.h2d_bytes = 0       # bytes moved by the host-buffer entry points (bench.py reports them)
+        self.d2h_bytes = 0
 
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
@@ -62,6 +66,34 @@ class CudaBackend(object):
         if y.numel() != self.n_proj * self.n_det:
             raise ValueError("projections have %d elements, operator expects %d" % (y.numel(), self.n_proj * self.n_det))
         return y
+
+    def _views_at(self, first):
+        """Device pointer of view record ``first`` (sub-tables are valid inputs of every operator)."""
+        return ctypes.c_void_p(self.views.data_ptr() + first * _lib.VIEW_STRIDE * 8)
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        t = self._dbuf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._dbuf[name] = t
+        return t
+
+    def _copy_stream(self):
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+        return self._copy
+
+    @staticmethod
+    def _host(x, dtype=torch.float32):
+        """numpy array or CPU tensor -> contiguous CPU tensor of ``dtype`` (no copy when already so)."""
+        t = torch.as_tensor(x)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    def _chunks(self, chunk_views):
+        c = max(1, int(chunk_views) if chunk_views else max(1, (self.n_proj + 7) // 8))
+        return [(a, min(self.n_proj, a + c)) for a in range(0, self.n_proj, c)]
 
     # -- poses ---------------------------------------------------------------------------------
     def set_poses(self, poses):
@@ -113,6 +145,112 @@ class CudaBackend(object):
         _lib.check(rc, "tomo_back_adjoint")
         self.launches += 1
         return out
+
+    # -- host-buffer entry points: copies overlapped with the kernels in view chunks ------------------
+    def forward_host(self, x_host, out_host=None, chunk_views=None):
+        """proj = A x with HOST input and output (numpy or CPU tensors; pinned memory makes the copies
+        asynchronous).  The volume goes up once; the views are projected in chunks and each chunk's
+        device->host copy runs on a side stream under the next chunk's kernel."""
+        x_host = self._host(x_host).reshape(-1)
+        if x_host.numel() != int(np.prod(self.vol_shape)):
+            raise ValueError("volume has %d elements, geometry expects %d" % (x_host.numel(), int(np.prod(self.vol_shape))))
+        if out_host is None:
+            out_host = torch.empty((self.n_proj,) + self.det_shape, dtype=torch.float32, pin_memory=True)
+        out3 = out_host.reshape((self.n_proj,) + self.det_shape)
+        cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
+        vol_d = self._buf("vol", self.vol_shape)
+        vol_d.reshape(-1).copy_(x_host, non_blocking=True)
+        volpad = self.pad(vol_d)
+        proj_d = self._buf("proj", (self.n_proj,) + self.det_shape)
+        with torch.cuda.device(self.device):
+            for a, b in self._chunks(chunk_views):
+                rc = self.lib.tomo_forward(self._g(), self._views_at(a), b - a, _ptr(volpad), _ptr(proj_d[a:b]), self._stream())
+                _lib.check(rc, "tomo_forward")
+                self.launches += 1
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(cp):
+                    cp.wait_event(ev)
+                    out3[a:b].copy_(proj_d[a:b], non_blocking=True)
+        cp.synchronize()
+        cur.wait_stream(cp)
+        self.h2d_bytes += 4 * x_host.numel()
+        self.d2h_bytes += 4 * out3.numel()
+        return out_host
+
+    def adjoint_host(self, y_host, out_host=None, chunk_views=None):
+        """vol = A^T y with HOST input and output: projection chunks go up on a side stream while the
+        previous chunk is backprojected (accumulating launches), the volume comes down once."""
+        y_host = self._host(y_host)
+        if y_host.numel() != self.n_proj * self.n_det:
+            raise ValueError("projections have %d elements, operator expects %d" % (y_host.numel(), self.n_proj * self.n_det))
+        y_host = y_host.reshape(self.n_proj, -1)
+        if out_host is None:
+            out_host = torch.empty(self.vol_shape, dtype=torch.float32, pin_memory=True)
+        cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
+        y_d = self._buf("proj", (self.n_proj,) + self.det_shape).reshape(self.n_proj, -1)
+        vol_d = self._buf("vol", self.vol_shape)
+        chunks = self._chunks(chunk_views)
+        cp.wait_stream(cur)                      # y_d / vol_d may still be in use by earlier work on `cur`
+        evs = []
+        with torch.cuda.stream(cp):
+            for a, b in chunks:
+                y_d[a:b].copy_(y_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                evs.append(ev)
+        with torch.cuda.device(self.device):
+            for k, (a, b) in enumerate(chunks):
+                cur.wait_event(evs[k])
+                rc = self.lib.tomo_back_adjoint(self._g(), self._views_at(a), b - a, _ptr(y_d[a:b]), _ptr(vol_d),
+                                                int(k > 0), self._stream())
+                _lib.check(rc, "tomo_back_adjoint")
+                self.launches += 2
+        out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
+        cur.synchronize()
+        self.h2d_bytes += 4 * y_host.numel()
+        self.d2h_bytes += 4 * out_host.numel()
+        return out_host
+
+    def proj_grad_host(self, vol_host, meas_host, chunk_views=None):
+        """Fused residual gradients with HOST inputs: returns (grad6 (n_proj, 6), cost (n_proj,)) float64 CPU
+        tensors.  The measured projections go up in chunks under the previous chunk's kernel."""
+        vol_host = self._host(vol_host).reshape(-1)
+        meas_host = self._host(meas_host)
+        if vol_host.numel() != int(np.prod(self.vol_shape)) or meas_host.numel() != self.n_proj * self.n_det:
+            raise ValueError("volume / measured projections do not match the geometry and the current poses")
+        meas_host = meas_host.reshape(self.n_proj, -1)
+        cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
+        vol_d = self._buf("vol", self.vol_shape)
+        m_d = self._buf("proj", (self.n_proj,) + self.det_shape).reshape(self.n_proj, -1)
+        grad6 = self._buf("grad6", (self.n_proj, 6), torch.float64)
+        cost = self._buf("cost", (self.n_proj,), torch.float64)
+        chunks = self._chunks(chunk_views)
+        cp.wait_stream(cur)
+        evs = []
+        with torch.cuda.stream(cp):
+            for a, b in chunks:
+                m_d[a:b].copy_(meas_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                evs.append(ev)
+        vol_d.reshape(-1).copy_(vol_host, non_blocking=True)
+        volpad = self.pad(vol_d)
+        cmax = max(b - a for a, b in chunks)
+        ws_bytes = self.lib.tomo_proj_grad_workspace_bytes(self._g(), cmax)
+        if self._ws is None or self._ws.numel() * 8 < ws_bytes:
+            self._ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            for k, (a, b) in enumerate(chunks):
+                cur.wait_event(evs[k])
+                rc = self.lib.tomo_proj_grad(self._g(), self._views_at(a), b - a, _ptr(volpad), _ptr(m_d[a:b]), None, None,
+                                             _ptr(grad6[a:b]), _ptr(cost[a:b]), _ptr(self._ws), ws_bytes, self._stream())
+                _lib.check(rc, "tomo_proj_grad")
+                self.launches += 2
+        g6, c = grad6.cpu(), cost.cpu()          # synchronises `cur`
+        self.h2d_bytes += 4 * (vol_host.numel() + meas_host.numel())
+        self.d2h_bytes += 8 * (g6.numel() + c.numel())
+        return g6, c
 
     def voxel_back(self, y, origin=None, out=None, accumulate=False):
         """Orphan voxel-driven bilinear backprojector (src/back_projection.f90)."""

@@ -10,9 +10,9 @@ reference's solvers use the matrix:
     sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A), y)      recon/sirt.py:61, cgls.py:54
     A.shape
 
-numpy in -> numpy out (host<->device copies inside the call, like a scipy matvec on host arrays);
-torch tensor in -> torch CUDA tensor out (no copy for a CUDA tensor, an asynchronous H2D copy for a
-(pinned) host tensor; what device-resident solvers and bench.py use).  All arithmetic runs in libtomo_b200.so on the GPU; there is no CPU
+numpy in -> numpy out, CPU tensor in -> (pinned) CPU tensor out: host<->device copies happen inside the
+call, overlapped with the kernels in view chunks (like a scipy matvec on host arrays, minus the wait);
+CUDA tensor in -> CUDA tensor out, no copies (device-resident solvers, bench.py's kernel timing).  All arithmetic runs in libtomo_b200.so on the GPU; there is no CPU
 path -- without CUDA, applying the operator raises.
 """
 import numpy as np
@@ -131,6 +131,10 @@ class ProjectionOperator(object):
             raise ValueError("dimension mismatch: operator has %d columns, vector has %d entries"
                              % (self._n_vox, _numel(x)))
         was_torch = _is_torch(x)
+        if not (was_torch and x.is_cuda) and self._mask is None and hasattr(self._backend, "forward_host"):
+            # host buffers: copies overlapped with the kernels in view chunks (cuda_backend.forward_host)
+            y = self._backend.forward_host(x).reshape(-1)
+            return y if was_torch else y.numpy().astype(np.result_type(self._precision, np.asarray(x).dtype), copy=False)
         xd = self._backend._as_vol(x if was_torch else np.ascontiguousarray(np.asarray(x), dtype=np.float32))
         if self._mask is not None:
             # dropping the masked columns' entries (projection_operators.py:60-70) == zeroing x there
@@ -145,6 +149,9 @@ class ProjectionOperator(object):
             raise ValueError("dimension mismatch: operator has %d rows, vector has %d entries"
                              % (self._n_proj * self._n_det, _numel(y)))
         was_torch = _is_torch(y)
+        if not (was_torch and y.is_cuda) and self._mask is None and hasattr(self._backend, "adjoint_host"):
+            v = self._backend.adjoint_host(y).reshape(-1)
+            return v if was_torch else v.numpy().astype(np.result_type(self._precision, np.asarray(y).dtype), copy=False)
         yd = self._backend._as_proj(y if was_torch else np.ascontiguousarray(np.asarray(y), dtype=np.float32))
         v = self._backend.adjoint(yd).reshape(-1)
         if self._mask is not None:
