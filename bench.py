@@ -305,8 +305,18 @@ def run_b200(a):
                "ray_kernel<gradient>": (t_g, bytes_g)}
     dom = max(kernels, key=lambda k: kernels[k][0])
     ach = kernels[dom][1] / (kernels[dom][0] * 1e-3) / 1e9
+    # measured DRAM traffic of the dominant kernel (ncu --set full capture of this exact workload, profiles/)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic_512x720.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        w = tj.get("workload", {})
+        if (w.get("size"), w.get("views"), w.get("n_gpus")) == (n, n_proj, world):
+            traffic = tj["kernels"].get(dom, {}).get("traffic_bytes")
+            traffic_src = "profiles/r1_traffic_512x720.json"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": kernels[dom][1], "peak_source": peak_src,
                 "per_kernel_ms": {k: v[0] for k, v in kernels.items()},
                 "per_kernel_algorithmic_gbs": {k: v[1] / (v[0] * 1e-3) / 1e9 for k, v in kernels.items()},
                 "step_frac_of_peak": (bytes_f + bytes_b + bytes_g) * world / (ms_per_step * 1e-3) / 1e9 / peak / world}
