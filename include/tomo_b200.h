@@ -45,7 +45,7 @@ extern "C" {
 #define TOMO_E_RANGE      (-4)           /* size exceeds 32-bit index budget of the kernels */
 
 /* Doubles per view in the device-side view table written by tomo_views_*. */
-#define TOMO_VIEW_STRIDE  96
+#define TOMO_VIEW_STRIDE  160
 #define TOMO_POSE_STRIDE  9
 /* Zero border (voxels) of the padded volume on every side of every axis. */
 #define TOMO_PAD          2
@@ -112,6 +112,21 @@ TOMO_API int tomo_back_adjoint_gather(const TomoGeom* geom, const void* views_de
 TOMO_API int tomo_back_voxel_bilinear(const TomoGeom* geom, const void* views_dev, int n_proj,
                              const double origin[3], const float* proj_dev, float* vol_dev,
                              int accumulate, void* stream);
+
+/* Voxel-driven forward projection ("splat") with optional gradient image, the orphan path of
+ * utilities/voxel_utilities.py:82-108 -> bilinear_vox_interp (src/vox_wt_grad.f90:1-55): every voxel centre
+ * is mapped with x' = Ry(b)(Rx(a)Rz(p)x + t), floor/fraction are taken relative to vox_origin - cor_shift
+ * (x and z components) and rec * bilinear weight is added to the 4 detector taps, each bounds-checked on its
+ * own; the gradient image adds rec * (g_x * dW/dx' + g_z * dW/dz') with g = derivative_rigid
+ * (voxel_utilities.py:23-48), rows [sx, sy, sz, theta(phi), alpha, beta].
+ *   det_dev   [n_proj][ndz][ndx]      float32  (x FASTEST: the Fortran's det_img(fz, fx), transposed w.r.t. the
+ *                                               ray-driven projections)
+ *   grad_dev  [n_proj][6][ndz][ndx]   float32, nullable
+ * Outputs are zeroed by the call.  This is a scatter: contributions are accumulated with float32 atomic adds,
+ * so the summation ORDER (not the set of terms) varies between runs -- results agree to float32 rounding, not
+ * bitwise.  vol_dev is the UNPADDED volume. */
+TOMO_API int tomo_voxel_splat(const TomoGeom* geom, const void* views_dev, int n_proj, const float* vol_dev,
+                     float* det_dev, float* grad_dev, void* stream);
 
 /* Projection + 6-DOF rigid-body gradient for all views in one launch.  Replaces
  * ProjectionMatrix.projection_gradient (utilities/projection_operators.py:112-122) ->

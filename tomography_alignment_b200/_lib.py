@@ -11,7 +11,7 @@ from .geometry import TomoGeom
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtomo_b200.so")
-VIEW_STRIDE = 96
+VIEW_STRIDE = 160
 POSE_STRIDE = 9
 PAD = 2
 
@@ -64,6 +64,8 @@ def load():
     L.tomo_back_adjoint_gather.argtypes = [G, vp, ci, vp, vp, ci, vp]
     L.tomo_back_voxel_bilinear.restype = ci
     L.tomo_back_voxel_bilinear.argtypes = [G, vp, ci, vp, vp, vp, ci, vp]
+    L.tomo_voxel_splat.restype = ci
+    L.tomo_voxel_splat.argtypes = [G, vp, ci, vp, vp, vp, vp]
     L.tomo_proj_grad_workspace_bytes.restype = sz
     L.tomo_proj_grad_workspace_bytes.argtypes = [G, ci]
     L.tomo_proj_grad.restype = ci

@@ -291,6 +291,53 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     }
 }
 
+// Voxel-driven forward splat + gradient image (src/vox_wt_grad.f90:1-55).  One thread per (voxel, view);
+// lanes along z.  Scatter with float32 atomic adds (see include/tomo_b200.h for the determinism note).
+__global__ void __launch_bounds__(BZ * BY * BX)
+voxel_splat_kernel(const BackArgs A, const float* __restrict__ vol, float* __restrict__ det, float* __restrict__ grad)
+{
+    const int z = blockIdx.x * BZ + threadIdx.x;
+    const int yb = blockIdx.y % ((A.ny + BY - 1) / BY), view = blockIdx.y / ((A.ny + BY - 1) / BY);
+    const int y = yb * BY + threadIdx.y;
+    const int x = blockIdx.z * BX + threadIdx.z;
+    if (x >= A.nx || y >= A.ny || z >= A.nz) return;
+    const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+    const float rec = vol[((size_t)x * A.ny + y) * A.nz + z];
+    const double cx = A.vox0[0] + x * A.vpix[0], cy = A.vox0[1] + y * A.vpix[1], cz = A.vox0[2] + z * A.vpix[2];
+    const double ux = V[V_VROT + 0] * cx + V[V_VROT + 1] * cy + V[V_VROT + 2] * cz + V[V_VTR + 0] - V[V_SORG + 0];
+    const double uz = V[V_VROT + 6] * cx + V[V_VROT + 7] * cy + V[V_VROT + 8] * cz + V[V_VTR + 2] - V[V_SORG + 1];
+    const double flx = floor(ux), flz = floor(uz);
+    const float ax = (float)(ux - flx), az = (float)(uz - flz);       // alpha_x, alpha_z are float32 in the reference
+    const int fx = (int)fmin(fmax(flx, -2.0), 1.0e9), fz = (int)fmin(fmax(flz, -2.0), 1.0e9);
+    const size_t n_det = (size_t)A.ndx * A.ndz;
+    float g0[6], g2[6];
+    if (grad) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double* q0 = V + V_SPL + (k * 2 + 0) * 4;
+            const double* q2 = V + V_SPL + (k * 2 + 1) * 4;
+            g0[k] = (float)(q0[0] * cx + q0[1] * cy + q0[2] * cz + q0[3]);
+            g2[k] = (float)(q2[0] * cx + q2[1] * cy + q2[2] * cz + q2[3]);
+        }
+    }
+    // taps (fx,fz), (fx+1,fz), (fx,fz+1), (fx+1,fz+1): weights and d/dx', d/dz' factors of vox_wt_grad.f90:25-50
+    const int   tx[4] = {fx, fx + 1, fx, fx + 1}, tzz[4] = {fz, fz, fz + 1, fz + 1};
+    const float w[4]  = {(1.f - ax) * (1.f - az), ax * (1.f - az), (1.f - ax) * az, ax * az};
+    const float G0[4] = {(1.f - az), -(1.f - az), az, -az};
+    const float G2[4] = {(1.f - ax), ax, -(1.f - ax), -ax};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (tx[t] < 0 || tx[t] >= A.ndx || tzz[t] < 0 || tzz[t] >= A.ndz) continue;
+        const size_t di = (size_t)tzz[t] * A.ndx + tx[t];
+        atomicAdd(det + (size_t)view * n_det + di, rec * w[t]);
+        if (grad) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                atomicAdd(grad + ((size_t)view * 6 + k) * n_det + di, g0[k] * G0[t] * rec + g2[k] * G2[t] * rec);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" void tomo_set_error(const char* msg);
@@ -349,4 +396,21 @@ extern "C" int tomo_back_voxel_bilinear(const TomoGeom* g, const void* views, in
     for (int a = 0; a < 3; ++a) A.origin[a] = origin[a];
     voxel_bilinear_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A);
     return tomo_check_cuda(cudaGetLastError(), "voxel_bilinear_kernel");
+}
+
+extern "C" int tomo_voxel_splat(const TomoGeom* g, const void* views, int n_proj, const float* vol,
+                                float* det, float* grad, void* stream)
+{
+    BackArgs A; dim3 grid;
+    if (!det) { tomo_set_error("tomo_voxel_splat: det_dev is NULL"); return TOMO_E_ARG; }
+    if (int e = fill_back(g, views, n_proj, vol, det, 0, &A, &grid)) return e;
+    const size_t n_det = (size_t)g->ndx * g->ndz;
+    cudaError_t ce = cudaMemsetAsync(det, 0, sizeof(float) * n_det * n_proj, (cudaStream_t)stream);
+    if (ce == cudaSuccess && grad) ce = cudaMemsetAsync(grad, 0, sizeof(float) * 6 * n_det * n_proj, (cudaStream_t)stream);
+    if (int e = tomo_check_cuda(ce, "tomo_voxel_splat: cudaMemsetAsync")) return e;
+    const unsigned nyb = (g->ny + BY - 1) / BY;
+    if ((double)nyb * n_proj > 65535.0) { tomo_set_error("tomo_voxel_splat: ny/4 * n_proj exceeds the launch grid"); return TOMO_E_RANGE; }
+    grid.y = nyb * n_proj;
+    voxel_splat_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A, vol, det, grad);
+    return tomo_check_cuda(cudaGetLastError(), "voxel_splat_kernel");
 }

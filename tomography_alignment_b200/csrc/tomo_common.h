@@ -28,7 +28,10 @@ enum {
     V_NCOL = 86,   // 1   ray colour classes of the tile-scatter backprojector (0: not applicable)
     V_NUNCOL = 87, // 1   number of views of the whole table with V_NCOL == 0 (same in every record, so a
                    //     pointer to any record is a valid sub-table)
-    V_END  = 88
+    V_SPL  = 96,   // 48  voxel-driven derivative_rigid (voxel_utilities.py:23-48): [k][c][4], k = sx,sy,sz,theta,alpha,beta,
+                   //     c = 0 (x' row) / 1 (z' row): value = v[0]*cx + v[1]*cy + v[2]*cz + v[3] at voxel centre (cx,cy,cz)
+    V_SORG = 144,  // 2   vox_origin - cor_shift, x and z components (voxel_utilities.py:61,90)
+    V_END  = 146
 };
 
 static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");

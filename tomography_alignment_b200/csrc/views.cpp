@@ -166,6 +166,26 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
         const M3 Vr = mul(Rb, mul(Ra, Rp));
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[V_VROT + 3 * i + j] = Vr.m[i][j];
         put(o + V_VTR, mul(Rb, t));
+
+        // derivative_rigid (utilities/voxel_utilities.py:23-48), rows x' (0) and z' (2) only -- the Fortran never
+        // reads the y' row (src/vox_wt_grad.f90:27-29).  Each is affine in the voxel centre c:
+        //   k = 0..2: R_b[:, k]                      (constant)
+        //   k = 3   : (R_b R_a dR_t) c               k = 4: (R_b dR_a R_t) c
+        //   k = 5   : dR_b (R_a R_t c + t)
+        {
+            const M3 D3 = mul(mul(Rb, Ra), dRp), D4 = mul(Rb, mul(dRa, Rp)), D5 = mul(dRb, mul(Ra, Rp));
+            const V3 d5t = mul(dRb, t);
+            const int rowsel[2] = {0, 2};
+            for (int c = 0; c < 2; ++c) {
+                const int r_ = rowsel[c];
+                for (int k = 0; k < 3; ++k) { double* q = o + V_SPL + (k * 2 + c) * 4; q[0] = q[1] = q[2] = 0.0; q[3] = Rb.m[r_][k]; }
+                double* q3 = o + V_SPL + (3 * 2 + c) * 4; double* q4 = o + V_SPL + (4 * 2 + c) * 4; double* q5 = o + V_SPL + (5 * 2 + c) * 4;
+                for (int a = 0; a < 3; ++a) { q3[a] = D3.m[r_][a]; q4[a] = D4.m[r_][a]; q5[a] = D5.m[r_][a]; }
+                q3[3] = 0.0; q4[3] = 0.0; q5[3] = d5t.v[r_];
+            }
+            o[V_SORG + 0] = g->vox_origin[0] - ps[6];
+            o[V_SORG + 1] = g->vox_origin[2] - ps[8];
+        }
     }
     double n_uncoloured = 0.0;
     for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_NCOL] == 0.0) n_uncoloured += 1.0;

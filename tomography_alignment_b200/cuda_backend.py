@@ -267,6 +267,20 @@ class CudaBackend(object):
         self.launches += 1
         return out
 
+    def voxel_splat(self, vol, want_grad=True):
+        """Orphan voxel-driven forward splat (+ gradient image), src/vox_wt_grad.f90:1-55: returns
+        (det (n_proj, ndz, ndx), grad (n_proj, 6, ndz, ndx) or None), x fastest."""
+        vol = self._as_vol(vol)
+        ndx, ndz = self.det_shape
+        det = torch.empty((self.n_proj, ndz, ndx), dtype=torch.float32, device=self.device)
+        grad = torch.empty((self.n_proj, 6, ndz, ndx), dtype=torch.float32, device=self.device) if want_grad else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.tomo_voxel_splat(self._g(), _ptr(self.views), self.n_proj, _ptr(vol), _ptr(det), _ptr(grad),
+                                           self._stream())
+        _lib.check(rc, "tomo_voxel_splat")
+        self.launches += 1
+        return det, grad
+
     def proj_grad(self, vol, meas=None, want_proj=True, want_dproj=True, want_grad6=None, repad=True):
         """Projection + 6-DOF gradient for all current views (tomo_proj_grad).
 

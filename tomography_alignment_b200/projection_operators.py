@@ -214,6 +214,23 @@ class ProjectionMatrix(object):
         return (proj.cpu().numpy().astype(self.precision, copy=False),
                 grad.cpu().numpy().astype(self.precision, copy=False))
 
+    def voxel_projection_gradient(self, rec, alpha, beta, phi, xyz_shift, cor_shift):
+        """The voxel-driven twin the reference keeps next to the ray-driven path
+        (utilities/voxel_utilities.py:82-108, imported as vox_forward_proj_grad in projection_operators.py:8 but
+        never called): (det_img.ravel() with x fastest, gradient (6, n_det)), rows [sx, sy, sz, theta, alpha, beta]."""
+        if self._grad_backend is None:
+            from .cuda_backend import CudaBackend
+            self._grad_backend = self._backend if (self._backend is not None and not hasattr(self._backend, "views")) \
+                else CudaBackend(self.geometry, self._device)
+        cor = np.asarray(cor_shift, dtype=np.float64).reshape(-1)[:3].reshape(1, 3)
+        self._grad_backend.set_poses(pose_table(np.array([[phi, alpha, beta]], dtype=np.float64),
+                                                np.asarray(xyz_shift, dtype=np.float64).reshape(1, 3), cor))
+        det, grad = self._grad_backend.voxel_splat(rec, want_grad=True)
+        det, grad = det.reshape(-1), grad.reshape(6, -1)
+        if _is_torch(rec):
+            return det, grad
+        return (det.cpu().numpy().astype(self.precision, copy=False), grad.cpu().numpy().astype(self.precision, copy=False))
+
     def projection_gradient_batch(self, rec, angles, xyz_shift, cor_shift=None, meas=None,
                                   want_dproj=True, want_proj=True):
         """All views at once on the device (what the reference does with n_proj separate calls,

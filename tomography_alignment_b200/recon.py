@@ -1,0 +1,182 @@
+"""Device-resident reconstruction loops with the interfaces of the reference's ``recon/sirt.py`` and
+``recon/cgls.py``.
+
+The reference's solvers run unchanged on top of ``ProjectionMatrix``, but every
+``A x`` / ``A^T y`` then crosses the host<->device boundary.  These classes keep the iteration on the GPU:
+volume, projections, the SIRT normalisers W = 1/(A 1), V = 1/(A^T 1) and all norms live in device
+memory; only the per-iteration error scalars come back.  Constructor arguments, option keys, return
+values ``(rec.reshape(vox_shape), rms_error[:k])`` and the semi-convergence stop follow the reference
+line by line (recon/sirt.py:9-107, recon/cgls.py:9-104).
+
+With ``group`` (a torch.distributed process group; one rank per GPU) the views are sharded like
+recon/sirt_mpi.py:36-72 / cgls_mpi.py:36-60 and the backprojections are all-reduced.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .projection_operators import ProjectionMatrix, normalise_poses, pose_table
+from .sharding import shard_views
+
+
+class _DeviceSolver(object):
+    def __init__(self, geometry, projections, angles, xyz_shifts, options=None, group=None, device=None,
+                 backend=None):
+        options = {} if options is None else options
+        self.geometry = geometry
+        self.angles = np.asarray(angles, dtype=np.float64)
+        self.xyz_shifts = np.asarray(xyz_shifts, dtype=np.float64)
+        self.n_proj = self.angles.shape[0]
+        self.precision = options['precision'] if 'precision' in options else np.float32
+        self.voxel_mask = options['voxel_mask'] if 'voxel_mask' in options else None
+        self.group = group
+        self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.my_index = shard_views(self.n_proj, self.world, self.rank)
+        self.my_n_proj = int(len(self.my_index))
+        if backend is None:
+            from .cuda_backend import CudaBackend
+            backend = CudaBackend(geometry, device)
+        self.backend = backend
+        self.device = getattr(backend, "device", torch.device("cpu"))
+        cor = np.asarray(geometry.cor_shift, dtype=np.float64).reshape(-1, 3)
+        self.backend.set_poses(pose_table(self.angles[self.my_index], self.xyz_shifts[self.my_index],
+                                          cor[self.my_index]))
+        self._dev = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a)).to(self.device, dt)
+        proj = np.asarray(projections).reshape(self.n_proj, -1)
+        self.projections = self._dev(proj[self.my_index])                 # this rank's measured views
+        gt = options['ground_truth'] if 'ground_truth' in options else None
+        self.ground_truth = None if gt is None else self._dev(np.asarray(gt).ravel())
+        rec = options['rec'] if 'rec' in options else None
+        self.rec = (torch.zeros(int(geometry.n_vox), dtype=torch.float32, device=self.device) if rec is None
+                    else self._dev(np.asarray(rec).ravel()).clone())
+        self.mask = None if self.voxel_mask is None else self._dev(np.asarray(self.voxel_mask).ravel().astype(np.float32))
+
+    # A x on this rank's views, A^T y summed over all ranks
+    def _A(self, x):
+        if self.mask is not None:
+            x = x * self.mask
+        return self.backend.forward(x).reshape(self.my_n_proj, -1)
+
+    def _At(self, y):
+        v = self.backend.adjoint(y).reshape(-1)
+        if self.world > 1:
+            dist.all_reduce(v, group=self.group)
+        if self.mask is not None:
+            v = v * self.mask
+        return v
+
+    def _sum(self, t):
+        """float64 sum over all ranks of a per-rank scalar tensor."""
+        t = t.double().reshape(1)
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def _norm_factor(self):
+        if self.ground_truth is not None:
+            return float(torch.linalg.vector_norm(self.ground_truth.double()))
+        return float(torch.sqrt(self._sum((self.projections.double() ** 2).sum())))
+
+    def _result(self, rms_error, k):
+        shape = tuple(int(v) for v in self.geometry.vox_shape)
+        return self.rec.reshape(shape).cpu().numpy().astype(self.precision, copy=False), rms_error[:k]
+
+
+class SIRT(_DeviceSolver):
+    """recon/sirt.py:7-107 on the device.
+
+    W = 1/(A 1), V = 1/(A^T 1) with zeros mapped to 0 (sirt.py:33-40; the *_mpi twin uses the threshold
+    1e-8, sirt_mpi.py:69-72, which is what runs when ``group`` is given);
+    x <- x + V * A^T (W * (b - A x)); optional positivity; stop when the RMS error rises (sirt.py:75-78)."""
+
+    def __init__(self, geometry, projections, angles, xyz_shifts, options=None, group=None, device=None, backend=None):
+        super().__init__(geometry, projections, angles, xyz_shifts, options, group, device, backend)
+        self._initialize()
+
+    def _initialize(self):
+        ones_v = torch.ones(int(self.geometry.n_vox), dtype=torch.float32, device=self.device)
+        W = self._A(ones_v)
+        V = self._At(torch.ones_like(W))
+        thr = 1.e-8 if self.world > 1 else 0.0
+        self.W = torch.where(W > thr, 1.0 / W, torch.zeros_like(W)) if self.world > 1 else \
+            torch.where(W == 0.0, torch.zeros_like(W), 1.0 / W)
+        self.V = torch.where(V > thr, 1.0 / V, torch.zeros_like(V)) if self.world > 1 else \
+            torch.where(V == 0.0, torch.zeros_like(V), 1.0 / V)
+
+    def run_main_iteration(self, niter=100, make_plot=False, projections=None, positivity=False, debug=False):
+        if projections is not None:
+            self.projections = self._dev(np.asarray(projections).reshape(self.n_proj, -1)[self.my_index])
+        norm_factor = self._norm_factor()
+        rms_error = np.zeros((niter,))
+        self.convergence = np.zeros((niter,))
+        stop, k = 0, 0
+        first_check = 1 if self.world > 1 else 0        # sirt.py:75 tests k > 0, sirt_mpi.py:118 tests k > 1
+        while k < niter and not stop:
+            res = self.projections - self._A(self.rec)
+            back_proj = self._At(self.W * res)
+            self.rec += back_proj * self.V
+            if positivity:
+                self.rec.clamp_(min=0.0)
+            self.convergence[k] = float(torch.sqrt(self._sum((res.double() ** 2).sum())))
+            if self.ground_truth is None:
+                rms_error[k] = self.convergence[k] / norm_factor
+            else:
+                rms_error[k] = float(torch.linalg.vector_norm((self.ground_truth - self.rec).double())) / norm_factor
+            if k > first_check and rms_error[k] > rms_error[k - 1]:
+                stop = 1
+                if self.rank == 0:
+                    print('semi-convergence criterion reached: stopping at k %3d with RMSE = %4.5f' % (k, rms_error[k]))
+            k += 1
+        return self._result(rms_error, k)
+
+
+class CGLS(_DeviceSolver):
+    """recon/cgls.py:7-104 on the device (the reference file does not run as shipped: it imports a module that
+    is not in the repository and reads an undefined attribute; the iteration itself is restated):
+        r = b - A x, p = A^T r, gamma = |p|^2
+        q = A p; alpha = gamma/|q|^2; x += alpha p; r -= alpha q; s = A^T r; beta = |s|^2/gamma; p = s + beta p
+    with the reference's restart when the residual rises (cgls.py:59-67)."""
+
+    def __init__(self, geometry, projections, angles, xyz_shift, options=None, group=None, device=None, backend=None):
+        super().__init__(geometry, projections, angles, xyz_shift, options, group, device, backend)
+        self.rms_error = None
+        self._initialize()
+
+    def _initialize(self):
+        self._r = self.projections - self._A(self.rec)
+        self._p = self._At(self._r)
+        self._gamma = float((self._p.double() ** 2).sum())
+
+    def run_main_iteration(self, make_plot=False, niter=100, debug=False):
+        norm_factor = self._norm_factor()
+        conv = np.zeros((niter,))
+        self.rms_error = np.zeros((niter,))
+        stop, k, reinit_iter = 0, 0, 0
+        while not stop and k < niter:
+            q = self._A(self._p)
+            alpha = self._gamma / float(self._sum((q.double() ** 2).sum()))
+            self.rec += alpha * self._p
+            conv[k] = float(torch.sqrt(self._sum(((self.projections - self._A(self.rec)).double() ** 2).sum())))
+            if k > 0 and conv[k] > conv[k - 1]:
+                if self.rank == 0:
+                    print('reinitializing at iteration %d' % k)
+                if reinit_iter + 1 == k:
+                    if self.rank == 0:
+                        print('need to re-initialize at two consecutive iterations: quitting')
+                    return self._result(self.rms_error, k)
+                self.rec -= alpha * self._p
+                self._initialize()
+                reinit_iter = k
+            self._r -= alpha * q
+            s = self._At(self._r)
+            gamma = float((s.double() ** 2).sum())
+            beta = gamma / self._gamma
+            self._gamma = gamma
+            self._p = s + beta * self._p
+            if self.ground_truth is None:
+                self.rms_error[k] = float(torch.sqrt(self._sum((self._r.double() ** 2).sum()))) / norm_factor
+            else:
+                self.rms_error[k] = float(torch.linalg.vector_norm((self.rec - self.ground_truth).double())) / norm_factor
+            k += 1
+        return self._result(self.rms_error, k)
