@@ -301,8 +301,8 @@ def run_b200(a):
     bytes_f = my_n * (4 * n_vox + 4 * n_det)
     bytes_b = my_n * (4 * n_vox + 4 * n_det)
     bytes_g = my_n * (4 * n_vox + 4 * n_det) + 48 * my_n
-    kernels = {"ray_kernel<forward>": (t_f, bytes_f), "adjoint_tile_kernel": (t_b, bytes_b),
-               "ray_kernel<gradient>": (t_g, bytes_g)}
+    kernels = {"ray_kernel_forward": (t_f, bytes_f), "adjoint_tile_kernel": (t_b, bytes_b),
+               "ray_kernel_gradient": (t_g, bytes_g)}
     dom = max(kernels, key=lambda k: kernels[k][0])
     ach = kernels[dom][1] / (kernels[dom][0] * 1e-3) / 1e9
     # measured DRAM traffic of the dominant kernel (ncu --set full capture of this exact workload, profiles/)

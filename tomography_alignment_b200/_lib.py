@@ -10,7 +10,7 @@ import subprocess
 from .geometry import TomoGeom
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtomo_b200.so")
+LIB_PATH = os.environ.get("TOMO_B200_LIB", os.path.join(_HERE, "libtomo_b200.so"))   # override: tuning builds only
 VIEW_STRIDE = 160
 POSE_STRIDE = 9
 PAD = 2

@@ -86,8 +86,17 @@ voxel_bilinear_kernel(const BackArgs A)
 }
 
 
-constexpr int TNW = 8;     // warps per block of the tile kernel
-constexpr int TSX = TOMO_BT_X + 4, TSY = TOMO_BT_Y + 4, TSZ = TOMO_BT_Z + 4;   // smem tile incl. 2 ghost cells per side
+constexpr int TNW = TOMO_BT_WARPS;     // warps per block of the tile kernel
+// Shared-memory tile: one ghost cell per side, [TSX][TSY][TSZ] with TSZ = 32 so that lanes that straddle two
+// rows or planes still hit 32 distinct banks.  A sample whose float32-marched cell lands one cell outside the
+// active range (only possible within ~1e-5 of the boundary) writes one cell further out: along z and y that
+// address wraps into a ghost cell of the neighbouring row / plane, along x into the guard planes allocated
+// before and after the tile.  Ghost and guard cells are never read back, so such writes (and races on
+// them) cannot reach an interior voxel.
+constexpr int TSX = TOMO_BT_X + 2, TSY = TOMO_BT_Y + 2, TSZ = TOMO_BT_Z + 2;
+constexpr int TGUARD = TSY * TSZ + TSZ + 1;                  // floats before and after the tile
+constexpr int TSMEM_FLOATS = TSX * TSY * TSZ + 2 * TGUARD;
+static_assert(TSZ == 32, "the tile kernel maps the z cells of a tile onto the 32 lanes / banks");
 
 // Per-view constants of the tile kernel, float32 and tile-local: p_s = Bc + di*U + dk*W + dj*D with
 // di = ix - ix_lo, dk = iz - iz_lo, dj = j - jc (all small), p_s in smem-cell coordinates.
@@ -100,6 +109,33 @@ struct TileView {
     float dupthr;           // same-z-cell test threshold for adjacent lanes
 };
 
+// Four read-modify-writes acc[off_k] += w_k * wz on shared memory, predicated on `act`, as one PTX block:
+// no branch, no reconvergence barrier; the four loads are issued before the first store.
+template <int O1, int O2, int O3>
+__device__ __forceinline__ void rmw4(float* s, bool act, float w0, float w1, float w2, float w3, float wz)
+{
+#if defined(TOMO_TILE_PTX_RMW)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(s);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f32 a0, a1, a2, a3;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p ld.shared.f32 a0, [%1];\n\t@p ld.shared.f32 a1, [%1+%7];\n\t"
+        "@p ld.shared.f32 a2, [%1+%8];\n\t@p ld.shared.f32 a3, [%1+%9];\n\t"
+        "fma.rn.f32 a0, %2, %6, a0;\n\tfma.rn.f32 a1, %3, %6, a1;\n\t"
+        "fma.rn.f32 a2, %4, %6, a2;\n\tfma.rn.f32 a3, %5, %6, a3;\n\t"
+        "@p st.shared.f32 [%1], a0;\n\t@p st.shared.f32 [%1+%7], a1;\n\t"
+        "@p st.shared.f32 [%1+%8], a2;\n\t@p st.shared.f32 [%1+%9], a3;\n\t}"
+        :: "r"((unsigned)act), "r"(a), "f"(w0), "f"(w1), "f"(w2), "f"(w3), "f"(wz),
+           "n"(O1 * 4), "n"(O2 * 4), "n"(O3 * 4) : "memory");
+#else
+    if (act) {
+        const float a0 = s[0], a1 = s[O1], a2 = s[O2], a3 = s[O3];
+        s[0] = fmaf(w0, wz, a0); s[O1] = fmaf(w1, wz, a1);
+        s[O2] = fmaf(w2, wz, a2); s[O3] = fmaf(w3, wz, a3);
+    }
+#endif
+}
+
 // March the rays of one view through the tile.  SGX/SGY/SGZ = sign of D per axis: with the mirrored
 // frame q = SG * p_s the carries are one-sided and the 7 corner offsets are compile-time immediates.
 template <int SGX, int SGY, int SGZ>
@@ -109,7 +145,7 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int STX = SGX * TSY * TSZ, STY = SGY * TSZ, STZ = SGZ;
     constexpr int O01 = STY, O10 = STX, O11 = STX + STY, OZ = STZ;
-    const float hi[3] = {(float)(TOMO_BT_X + 2), (float)(TOMO_BT_Y + 2), (float)(TOMO_BT_Z + 2)};
+    const float hi[3] = {(float)(TOMO_BT_X + 1), (float)(TOMO_BT_Y + 1), (float)(TOMO_BT_Z + 1)};
     const int stepoff = tv.di_step;
     for (int c = 0; c < tv.ncol; ++c) {
         const int first = tv.ix_lo + (((c - tv.ix_lo) % tv.ncol) + tv.ncol) % tv.ncol;
@@ -121,14 +157,14 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                 float pr[3];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) pr[a] = fmaf(fdk, tv.W[a], fmaf(fdi, tv.U[a], tv.Bc[a]));
-                // per-lane sample range (relative to jc) inside the tile's active box 1 <= p_s < T+2
+                // per-lane sample range (relative to jc) inside the tile's active box 0 <= p_s < T+1
                 float jlo = (float)tv.djmin, jhi = (float)tv.djmax;
                 bool empty = !valid;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    if (tv.D[a] > 0.f)      { jlo = fmaxf(jlo, (1.f - pr[a]) * tv.invD[a]);   jhi = fminf(jhi, (hi[a] - pr[a]) * tv.invD[a]); }
-                    else if (tv.D[a] < 0.f) { jlo = fmaxf(jlo, (hi[a] - pr[a]) * tv.invD[a]); jhi = fminf(jhi, (1.f - pr[a]) * tv.invD[a]); }
-                    else if (pr[a] < 1.f || pr[a] >= hi[a]) empty = true;
+                    if (tv.D[a] > 0.f)      { jlo = fmaxf(jlo, (0.f - pr[a]) * tv.invD[a]);   jhi = fminf(jhi, (hi[a] - pr[a]) * tv.invD[a]); }
+                    else if (tv.D[a] < 0.f) { jlo = fmaxf(jlo, (hi[a] - pr[a]) * tv.invD[a]); jhi = fminf(jhi, (0.f - pr[a]) * tv.invD[a]); }
+                    else if (pr[a] < 0.f || pr[a] >= hi[a]) empty = true;
                 }
                 jlo = fminf(fmaxf(jlo, -1.0e6f), 1.0e6f);
                 jhi = fminf(fmaxf(jhi, -1.0e6f), 1.0e6f);
@@ -159,17 +195,9 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                     const float wy0 = 1.f - f1, wz0 = 1.f - f2;
                     const float w00 = wx0 * wy0, w01 = wx0 * f1, w10 = wx1 * wy0, w11 = wx1 * f1;
                     if (!__any_sync(FULL, dup)) {
-                        if (act) {
-                            const float a0 = s[0], a1 = s[O01], a2 = s[O10], a3 = s[O11];
-                            s[0] = fmaf(w00, wz0, a0); s[O01] = fmaf(w01, wz0, a1);
-                            s[O10] = fmaf(w10, wz0, a2); s[O11] = fmaf(w11, wz0, a3);
-                        }
+                        rmw4<O01, O10, O11>(s, act, w00, w01, w10, w11, wz0);
                         __syncwarp();
-                        if (act) {
-                            const float a0 = s[OZ], a1 = s[OZ + O01], a2 = s[OZ + O10], a3 = s[OZ + O11];
-                            s[OZ] = fmaf(w00, f2, a0); s[OZ + O01] = fmaf(w01, f2, a1);
-                            s[OZ + O10] = fmaf(w10, f2, a2); s[OZ + O11] = fmaf(w11, f2, a3);
-                        }
+                        rmw4<O01, O10, O11>(s + OZ, act, w00, w01, w10, w11, f2);
                         __syncwarp();
                     } else {
                         // rare (W_z < 1 makes two adjacent lanes share a z cell ~ once per 1/(1-W_z) samples):
@@ -177,17 +205,9 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
 #pragma unroll 1
                         for (int pass = 0; pass < 2; ++pass) {
                             const bool go = act && (dup == (pass == 1));
-                            if (go) {
-                                const float a0 = s[0], a1 = s[O01], a2 = s[O10], a3 = s[O11];
-                                s[0] = fmaf(w00, wz0, a0); s[O01] = fmaf(w01, wz0, a1);
-                                s[O10] = fmaf(w10, wz0, a2); s[O11] = fmaf(w11, wz0, a3);
-                            }
+                            rmw4<O01, O10, O11>(s, go, w00, w01, w10, w11, wz0);
                             __syncwarp();
-                            if (go) {
-                                const float a0 = s[OZ], a1 = s[OZ + O01], a2 = s[OZ + O10], a3 = s[OZ + O11];
-                                s[OZ] = fmaf(w00, f2, a0); s[OZ + O01] = fmaf(w01, f2, a1);
-                                s[OZ + O10] = fmaf(w10, f2, a2); s[OZ + O11] = fmaf(w11, f2, a3);
-                            }
+                            rmw4<O01, O10, O11>(s + OZ, go, w00, w01, w10, w11, f2);
                             __syncwarp();
                         }
                     }
@@ -209,18 +229,19 @@ __global__ void __launch_bounds__(TNW * 32)
 adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int ntz)
 {
     constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
-    extern __shared__ float acc[];                       // [TSX][TSY][TSZ]
+    extern __shared__ float smem_raw[];                  // guard | [TSX][TSY][TSZ] | guard
+    float* const acc = smem_raw + TGUARD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int bb = blockIdx.x;
     const int tz = bb % ntz; bb /= ntz;
     const int ty = bb % nty;
     const int tx = bb / nty;
-    const int org[3] = {tx * TX - 2, ty * TY - 2, tz * TZ - 2};   // voxel coordinate of smem cell 0
-    for (int i = threadIdx.x; i < TSX * TSY * TSZ; i += TNW * 32) acc[i] = 0.f;
+    const int org[3] = {tx * TX - 1, ty * TY - 1, tz * TZ - 1};   // voxel coordinate of smem cell 0 (the low ghost cell)
+    for (int i = threadIdx.x; i < TSMEM_FLOATS; i += TNW * 32) smem_raw[i] = 0.f;
     __syncthreads();
 
     const size_t n_det = (size_t)A.ndx * A.ndz;
-    // a sample is ours iff its floor cell lies in [1, T+1] per axis, i.e. 1 <= p_s < T+2 (smem coordinates)
+    // a sample is ours iff its floor cell lies in [0, T] per axis, i.e. 0 <= p_s < T+1 (smem coordinates)
     const double hw[3] = {0.5 * (TX + 1), 0.5 * (TY + 1), 0.5 * (TZ + 1)};
 
     for (int view = 0; view < A.n_proj; ++view) {
@@ -233,7 +254,7 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             B[a] = V[V_P00 + a] - (double)org[a];        // p_s = B + ix U + iz W + j D
-            cc[a] = 1.0 + hw[a] - B[a];
+            cc[a] = hw[a] - B[a];
         }
         double lc[3], lr[3];
 #pragma unroll
@@ -284,7 +305,7 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
         const int zz = i & 31, yy = (i >> 5) % TY, xx = (i >> 5) / TY;
         const int x = tx * TX + xx, y = ty * TY + yy, z = tz * TZ + zz;
         if (zz < TZ && x < A.nx && y < A.ny && z < A.nz) {
-            const float v = acc[((xx + 2) * TSY + (yy + 2)) * TSZ + zz + 2];
+            const float v = acc[((xx + 1) * TSY + (yy + 1)) * TSZ + zz + 1];
             const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
             A.vol[vi] = A.accumulate ? A.vol[vi] + v : v;
         }
@@ -372,7 +393,7 @@ extern "C" int tomo_back_adjoint(const TomoGeom* g, const void* views, int n_pro
     if (int e = fill_back(g, views, n_proj, proj, vol, accumulate, &A, &grid)) return e;
     constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
     const int ntx = (g->nx + TX - 1) / TX, nty = (g->ny + TY - 1) / TY, ntz = (g->nz + TZ - 1) / TZ;
-    const size_t smem = sizeof(float) * (TX + 4) * (TY + 4) * (TZ + 4);
+    const size_t smem = sizeof(float) * TSMEM_FLOATS;
     const double nblocks = (double)ntx * nty * ntz;
     if (nblocks >= 2147483647.0) { tomo_set_error("tomo_back_adjoint: too many tiles"); return TOMO_E_RANGE; }
     cudaError_t ce = cudaFuncSetAttribute(adjoint_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -29,7 +29,9 @@
 #define TOMO_LDG(p) (*(p))
 #endif
 
+#ifndef RAY_REBASE
 #define RAY_REBASE 64
+#endif
 
 struct RayDims {
     int nx, ny, nz;      // volume shape
@@ -163,6 +165,7 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
             if (f[a] >= 1.0f) { f[a] -= 1.0f; off += r.st[a]; }
         }
         const int jend = (jc + RAY_REBASE < r.j1) ? jc + RAY_REBASE : r.j1;
+#pragma unroll 2
         for (int j = jc; j < jend; ++j) {
             const float* __restrict__ c = vol + off;
             RAY_SAMPLE(c, f[0], f[1], f[2])

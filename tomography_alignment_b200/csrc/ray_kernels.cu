@@ -24,7 +24,10 @@
 namespace {
 
 constexpr int TILE_Z = 32;     // lanes: iz
-constexpr int TILE_X = 8;      // warps: ix
+#ifndef RAY_TILE_X
+#define RAY_TILE_X 8
+#endif
+constexpr int TILE_X = RAY_TILE_X;      // warps: ix
 constexpr int NRED   = 7;      // 6 gradient components + cost
 
 struct RayArgs {
@@ -40,8 +43,7 @@ struct RayArgs {
 };
 
 template <bool GRAD>
-__global__ void __launch_bounds__(TILE_Z * TILE_X)
-ray_kernel(const RayArgs A)
+__device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
 {
     const int bid  = blockIdx.x;
     const int xt   = bid % A.nxt;
@@ -99,6 +101,11 @@ ray_kernel(const RayArgs A)
         }
     }
 }
+
+// Measured on B200 (profiles/README.md): the forward march is fastest at 48 registers (5 blocks/SM) with the
+// sample loop unrolled twice; the gradient march is insensitive to both and keeps ptxas' own budget.
+__global__ void __launch_bounds__(TILE_Z * TILE_X, 5) ray_kernel_forward(const RayArgs A) { ray_kernel_body<false>(A); }
+__global__ void __launch_bounds__(TILE_Z * TILE_X) ray_kernel_gradient(const RayArgs A) { ray_kernel_body<true>(A); }
 
 // Second pass of the deterministic reduction: one thread per (view, component) sums the block
 // partials of that view in (zt, xt) order.
@@ -186,8 +193,8 @@ extern "C" int tomo_forward(const TomoGeom* g, const void* views, int n_proj,
     if (!proj) { tomo_set_error("tomo_forward: proj_dev is NULL"); return TOMO_E_ARG; }
     A.proj = proj;
     const dim3 block(TILE_Z, TILE_X);
-    ray_kernel<false><<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
-    return tomo_check_cuda(cudaGetLastError(), "ray_kernel<forward>");
+    ray_kernel_forward<<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+    return tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward");
 }
 
 extern "C" size_t tomo_proj_grad_workspace_bytes(const TomoGeom* g, int n_proj)
@@ -215,8 +222,8 @@ extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
         A.partial = (double*)workspace;
     }
     const dim3 block(TILE_Z, TILE_X);
-    ray_kernel<true><<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
-    if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel<gradient>")) return e;
+    ray_kernel_gradient<<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+    if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_gradient")) return e;
     if (reduce) {
         const int n = n_proj * NRED;
         grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, n_proj, A.nxt, A.nzt, grad6, cost);
