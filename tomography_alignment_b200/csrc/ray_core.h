@@ -122,20 +122,45 @@ TOMO_HD float fix_to_float(unsigned hi)
 #endif
 }
 
-// The 8 zero-padded corner loads and the trilinear interpolant in nested-lerp form; also returns the
-// pieces the spatial gradient is built from.
-#define RAY_SAMPLE(c, fx_, fy_, fz_)                                                                  \
-    const float v000 = TOMO_LDG(c),       v001 = TOMO_LDG(c + oz);                                      \
-    const float v010 = TOMO_LDG(c + o01), v011 = TOMO_LDG(c + o01 + oz);                                \
-    const float v100 = TOMO_LDG(c + o10), v101 = TOMO_LDG(c + o10 + oz);                                \
-    const float v110 = TOMO_LDG(c + o11), v111 = TOMO_LDG(c + o11 + oz);                                \
-    const float dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;        \
-    const float a00 = fmaf(fz_, dz00, v000), a01 = fmaf(fz_, dz01, v010);                              \
-    const float a10 = fmaf(fz_, dz10, v100), a11 = fmaf(fz_, dz11, v110);                              \
-    const float dy0 = a01 - a00, dy1 = a11 - a10;                                                      \
-    const float b0 = fmaf(fy_, dy0, a00), b1 = fmaf(fy_, dy1, a10);                                    \
-    const float gx = b1 - b0;                                                                          \
-    const float val = fmaf(fx_, gx, b0);
+// Packed float32x2 arithmetic: Blackwell issues one FFMA2 / FADD2 for two float32 lanes of a register pair
+// (sm_100 intrinsics __ffma2_rn / __fadd2_rn); the kernels are issue-bound, so pairing the two x-corners of
+// every (y, z) corner halves the interpolation instructions.  Host build (tests/emu): same IEEE operations.
+struct f2 { float x, y; };
+TOMO_HD f2 f2_make(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+TOMO_HD f2 f2_fma(f2 a, f2 b, f2 c)
+{
+#if defined(__CUDA_ARCH__)
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    return f2_make(r.x, r.y);
+#else
+    return f2_make(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// b - a
+TOMO_HD f2 f2_sub(f2 b, f2 a)
+{
+#if defined(__CUDA_ARCH__)
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(-1.f, -1.f), make_float2(b.x, b.y));
+    return f2_make(r.x, r.y);
+#else
+    return f2_make(b.x - a.x, b.y - a.y);
+#endif
+}
+
+// The 8 zero-padded corner loads and the trilinear interpolant in nested-lerp form, the two x-corners of each
+// (y, z) corner packed in one register pair (.x = m-floor x, .y = m-ceil x).  Leaves behind the pieces the
+// spatial gradient is built from: dzA/dzB (z differences at y-floor / y-ceil), dy (y differences), gx, val.
+#define RAY_SAMPLE(c, fx_, fy2_, fz2_)                                                                \
+    const f2 loA = f2_make(TOMO_LDG(c),            TOMO_LDG(c + o10));                                  \
+    const f2 hiA = f2_make(TOMO_LDG(c + oz),       TOMO_LDG(c + o10 + oz));                             \
+    const f2 loB = f2_make(TOMO_LDG(c + o01),      TOMO_LDG(c + o11));                                  \
+    const f2 hiB = f2_make(TOMO_LDG(c + o01 + oz), TOMO_LDG(c + o11 + oz));                             \
+    const f2 dzA = f2_sub(hiA, loA), dzB = f2_sub(hiB, loB);                                            \
+    const f2 aA = f2_fma(fz2_, dzA, loA), aB = f2_fma(fz2_, dzB, loB);                                  \
+    const f2 dy = f2_sub(aB, aA);                                                                       \
+    const f2 b = f2_fma(fy2_, dy, aA);                                                                  \
+    const float gx = b.y - b.x;                                                                         \
+    const float val = fmaf(fx_, gx, b.x);
 
 // Forward only: (cell offset, float32 fraction) marching, re-based from float64 every RAY_REBASE
 // samples.  The interpolant is continuous, so a cell decision that is off by float32 rounding next
@@ -168,7 +193,7 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
 #pragma unroll 2
         for (int j = jc; j < jend; ++j) {
             const float* __restrict__ c = vol + off;
-            RAY_SAMPLE(c, f[0], f[1], f[2])
+            RAY_SAMPLE(c, f[0], f2_make(f[1], f[1]), f2_make(f[2], f[2]))
             acc += val;
             f[0] += df[0]; f[1] += df[1]; f[2] += df[2];
             off += r.stepoff;
@@ -205,18 +230,22 @@ TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __r
         fh[a] = (unsigned)(f64 >> 32); fl[a] = (unsigned)f64;
         dh[a] = (unsigned)(d64 >> 32); dl[a] = (unsigned)d64;
     }
-    float acc = 0.f, s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+    float acc = 0.f, s0z = 0.f, s1z = 0.f;
+    f2 s0xy = f2_make(0.f, 0.f), s1xy = f2_make(0.f, 0.f);
     float fj = (float)r.j0;
     for (int j = r.j0; j < r.j1; ++j) {
         const float fx = fix_to_float(fh[0]), fy = fix_to_float(fh[1]), fz = fix_to_float(fh[2]);
         const float* __restrict__ c = vol + off;
-        RAY_SAMPLE(c, fx, fy, fz)
+        const f2 fy2 = f2_make(fy, fy);
+        RAY_SAMPLE(c, fx, fy2, f2_make(fz, fz))
         acc += val;
-        const float gy = fmaf(fx, dy1 - dy0, dy0);
-        const float e0 = fmaf(fy, dz01 - dz00, dz00), e1 = fmaf(fy, dz11 - dz10, dz10);
-        const float gz = fmaf(fx, e1 - e0, e0);
-        s0x += gx; s0y += gy; s0z += gz;
-        s1x = fmaf(fj, gx, s1x); s1y = fmaf(fj, gy, s1y); s1z = fmaf(fj, gz, s1z);
+        const float gy = fmaf(fx, dy.y - dy.x, dy.x);
+        const f2 e = f2_fma(fy2, f2_sub(dzB, dzA), dzA);
+        const float gz = fmaf(fx, e.y - e.x, e.x);
+        // moments: (gx, gy) packed, gz scalar
+        const f2 gxy = f2_make(gx, gy);
+        s0xy = f2_fma(gxy, f2_make(1.f, 1.f), s0xy); s0z += gz;
+        s1xy = f2_fma(f2_make(fj, fj), gxy, s1xy); s1z = fmaf(fj, gz, s1z);
         fj += 1.0f;
         off += r.stepoff;
         off += (int)fix64_add(fh[0], fl[0], dh[0], dl[0]) * r.st[0];
@@ -224,8 +253,8 @@ TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __r
         off += (int)fix64_add(fh[2], fl[2], dh[2], dl[2]) * SGZ;
     }
     out.acc = acc;
-    out.s0[0] = s0x * (float)r.sg[0]; out.s0[1] = s0y * (float)r.sg[1]; out.s0[2] = s0z * (float)r.sg[2];
-    out.s1[0] = s1x * (float)r.sg[0]; out.s1[1] = s1y * (float)r.sg[1]; out.s1[2] = s1z * (float)r.sg[2];
+    out.s0[0] = s0xy.x * (float)r.sg[0]; out.s0[1] = s0xy.y * (float)r.sg[1]; out.s0[2] = s0z * (float)r.sg[2];
+    out.s1[0] = s1xy.x * (float)r.sg[0]; out.s1[1] = s1xy.y * (float)r.sg[1]; out.s1[2] = s1z * (float)r.sg[2];
 }
 
 template <bool GRAD>
