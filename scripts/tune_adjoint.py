@@ -9,6 +9,8 @@ n, n_proj = int(sys.argv[1]), int(sys.argv[2])
 which = sys.argv[3] if len(sys.argv) > 3 else "fbg"
 g = Geometry(n_proj, np.array([n, n, n]), np.ones(3), np.array([n, n]), np.ones(2))
 phi, alpha, beta, xyz = benchmark_poses(720)
+if os.environ.get("UNTILTED"):
+    alpha, beta = alpha * 0, beta * 0
 sel = np.linspace(0, 719, n_proj).astype(int)
 be = CudaBackend(g, "cuda:0")
 be.set_poses(pose_table(np.array([phi, alpha, beta]).T[sel], xyz[sel], g.cor_shift))

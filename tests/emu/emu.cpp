@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../tomography_alignment_b200/csrc/ray_core.h"
 #include "../../tomography_alignment_b200/csrc/back_core.h"
+#include "../../tomography_alignment_b200/csrc/sep_core.h"
 
 #define EMU_API extern "C" __attribute__((visibility("default")))
 
@@ -25,6 +26,25 @@ EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, c
     for (int v = 0; v < n_proj; ++v) {
         const double* V = views + (size_t)v * TOMO_VIEW_STRIDE;
         double red[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (!want_grad && V[V_SEP] != 0.0) {
+            // untilted view: the separable cores (sep_core.h), S for every padded plane then the 2-tap z interpolation
+            const int nzp = tomo_nzp(g->nz);
+#pragma omp parallel for schedule(dynamic, 8)
+            for (int ix = 0; ix < g->ndx; ++ix) {
+                std::vector<float> S(nzp);
+                SepSetup r;
+                sep_setup(V, dm, ix, r);
+                for (int zq = 0; zq < nzp; zq += 4) sep_march_xy(volpad, V, dm, r, zq, &S[zq]);
+                for (int iz = 0; iz < g->ndz; ++iz) {
+                    int fzp; float wz;
+                    sep_zcell(V, iz, fzp, wz);
+                    float val = 0.f;
+                    if (fzp >= 0 && fzp <= nzp - 2) val = fmaf(wz, S[fzp + 1] - S[fzp], S[fzp]);
+                    if (proj) proj[v * n_det + (size_t)ix * g->ndz + iz] = val;
+                }
+            }
+            continue;
+        }
 #pragma omp parallel for schedule(dynamic, 8)
         for (int ix = 0; ix < g->ndx; ++ix) {
             double loc[7] = {0, 0, 0, 0, 0, 0, 0};

@@ -78,6 +78,20 @@ def test_voxel_driven_bilinear_backprojector(shape, dshape, n_proj, kw):
     assert rel_l2(be.voxel_back(y).numpy(), ref) <= TOL_PROJ
 
 
+@pytest.mark.parametrize("shape,dshape,kw", [((16, 16, 16), (16, 16), dict()), ((14, 20, 37), (14, 37), dict(cor=[0.4, 0, 0])),
+                                              ((12, 12, 12), (18, 9), dict(shift=6.0)), ((16, 16, 16), (16, 16), dict(step=0.5))])
+def test_separable_forward_for_untilted_views(shape, dshape, kw):
+    """alpha = beta = 0 (the API's default poses): the separable cores of sep_core.h reproduce the oracle."""
+    n_proj = 7
+    g, og, be, op, _ = setup(shape, dshape, n_proj, tilt=0.0, phis=[0.0, 0.4, np.pi / 4, np.pi / 2, 2.0, 2.9, np.pi], **kw)
+    assert np.all(be.views[:, 146] == 1.0)                 # V_SEP set by tomo_views_compute_host
+    vol = np.random.default_rng(8).random(shape).astype(np.float32)
+    assert rel_l2(be.forward(vol).numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    # a tilted table is not flagged
+    g2, og2, be2, op2, _ = setup(shape, dshape, 3, tilt=0.01)
+    assert np.all(be2.views[:, 146] == 0.0)
+
+
 def test_exact_lattice_pose_phi0():
     """phi = alpha = beta = 0, t = 0: every sample sits on a lattice plane in x and z.  Projection = sum over y,
     and the one-sided derivatives agree with the reference because the floor of an exact integer is exact."""

@@ -336,6 +336,27 @@ def test_batched_alignment_recovers_jitter_on_gpu():
     assert np.abs(x[:, 2] - alpha).max() < 4e-3 and np.abs(x[:, 3] - beta).max() < 4e-3
 
 
+@pytest.mark.parametrize("shape,dshape,kw", [((16, 16, 16), (16, 16), dict()), ((14, 20, 37), (14, 37), dict(cor=[0.4, 0, 0])),
+                                              ((12, 12, 12), (18, 9), dict(shift=6.0)), ((40, 40, 300), (40, 300), dict()),
+                                              ((16, 16, 16), (16, 16), dict(step=0.5))])
+def test_separable_forward_for_untilted_views(shape, dshape, kw):
+    """alpha = beta = 0 (the default poses of projection_matrix): sep_forward_kernel, incl. volumes taller than one
+    z chunk (300 planes = 3 chunks) and a table that mixes tilted and untilted views."""
+    n_proj = 7
+    phis = [0.0, 0.4, np.pi / 4, np.pi / 2, 2.0, 2.9, np.pi]
+    g, og, be, op, _ = setup(shape, dshape, n_proj, tilt=0.0, phis=phis, **kw)
+    assert bool((be.views[:, 146] == 1.0).all())
+    vol = np.random.default_rng(8).random(shape).astype(np.float32)
+    assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    # mixed table: views 1, 4 tilted
+    phi, alpha, beta, xyz = random_poses(n_proj, 3, tilt=0.0, phis=phis)
+    alpha[[1, 4]] = [0.01, -0.02]
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    assert be.views[:, 146].cpu().tolist() == [1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0]
+    ref = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz).forward(vol)
+    assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), ref) <= TOL_PROJ
+
+
 def test_error_codes_surface_as_exceptions():
     from tomography_alignment_b200 import _lib
     g, _ = make_geoms((8, 8, 8), (8, 8), 2)

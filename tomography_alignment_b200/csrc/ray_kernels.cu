@@ -40,6 +40,7 @@ struct RayArgs {
     int nx, ny, nz, ndx, ndz, n_proj;
     int sxp, syp;            // padded strides (floats) of x and y; z stride is 1
     int nxt, nzt;            // detector tiles along x and z
+    int skip_separable;      // forward only: leave views with V_SEP == 1 to sep_forward_kernel
 };
 
 template <bool GRAD>
@@ -54,6 +55,7 @@ __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
     const bool active = (ix < A.ndx) && (iz < A.ndz);
 
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+    if (!GRAD && A.skip_separable && V[V_SEP] != 0.0) return;      // untilted view: sep_forward_kernel does it
     const size_t n_det = (size_t)A.ndx * A.ndz;
     const size_t ray = (size_t)ix * A.ndz + iz;
 
@@ -143,6 +145,8 @@ __global__ void pad_volume_kernel(const float* __restrict__ vol, float* __restri
 
 extern "C" void tomo_set_error(const char* msg);
 int tomo_check_cuda(cudaError_t e, const char* what);
+int tomo_forward_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* volpad, float* proj,
+                                  void* stream);
 
 static int check_sizes(const TomoGeom* g)
 {
@@ -174,7 +178,7 @@ static int fill_args(const TomoGeom* g, const void* views, int n_proj, const flo
     if (!g || !views || !volpad || n_proj <= 0) { tomo_set_error("ray operator: null pointer or n_proj <= 0"); return TOMO_E_ARG; }
     if (int e = check_sizes(g)) return e;
     A->volpad = volpad; A->views = (const double*)views;
-    A->meas = nullptr; A->proj = nullptr; A->dproj = nullptr; A->partial = nullptr;
+    A->meas = nullptr; A->proj = nullptr; A->dproj = nullptr; A->partial = nullptr; A->skip_separable = 0;
     A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz; A->n_proj = n_proj;
     A->syp = tomo_nzp(g->nz);
     A->sxp = (g->ny + 2 * TOMO_PAD) * A->syp;
@@ -192,9 +196,12 @@ extern "C" int tomo_forward(const TomoGeom* g, const void* views, int n_proj,
     if (int e = fill_args(g, views, n_proj, volpad, &A)) return e;
     if (!proj) { tomo_set_error("tomo_forward: proj_dev is NULL"); return TOMO_E_ARG; }
     A.proj = proj;
+    A.skip_separable = 1;
     const dim3 block(TILE_Z, TILE_X);
     ray_kernel_forward<<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
-    return tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward");
+    if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward")) return e;
+    // untilted views (alpha = beta = 0): separable kernel; both kernels return at once for views of the other kind
+    return tomo_forward_separable_launch(g, views, n_proj, volpad, proj, stream);
 }
 
 extern "C" size_t tomo_proj_grad_workspace_bytes(const TomoGeom* g, int n_proj)

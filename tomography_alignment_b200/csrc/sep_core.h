@@ -1,0 +1,115 @@
+// sep_core.h -- cores of the separable (untilted-view) forward projector.
+//
+// When alpha = beta = 0 (the default pose set of ProjectionMatrix.projection_matrix,
+// utilities/projection_operators.py:30-34, and every "known geometry" reconstruction) the sample lattice
+// p = P00 + ix U + iz W + j D has W = (0, 0, W_z) and U_z = D_z = 0: the z coordinate of a sample depends on iz
+// only, its (x, y) on (ix, j) only.  The trilinear sum then factors exactly:
+//     proj[ix, iz] = (1 - wz) S[ix, fz] + wz S[ix, fz + 1],   S[ix, z] = sum_j bilinear_xy(vol[:, :, z]; x_j, y_j)
+// (same terms as src/ray_wt_grad.f90:20-91, regrouped; the zero border of the padded volume again stands in for
+// the per-corner bounds checks).  S is evaluated for four z planes per thread with 128-bit loads: cell and
+// weights are computed once per (ix, j) instead of once per sample.
+#pragma once
+#include "ray_core.h"
+
+#define SEP_CHUNK 128                    // z planes staged per warp
+#define SEP_OUT   (SEP_CHUNK - 4)        // planes a chunk produces outputs for (needs S[z] and S[z+1])
+
+struct SepSetup {
+    double p[2], D[2];
+    int sg[2], st[2];
+    int j0, j1, stepoff;
+};
+
+// xy-only clip of ray ix: samples with -1 <= x < nx and -1 <= y < ny (any z)
+TOMO_HD void sep_setup(const double* __restrict__ V, const RayDims dm, int ix, SepSetup& r)
+{
+    const double N[2] = {(double)dm.nx, (double)dm.ny};
+    const int ust[2] = {dm.sxp, dm.syp};
+    double jlo = 0.0, jhi = V[V_N];
+    bool empty = false;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        r.p[a] = V[V_P00 + a] + (double)ix * V[V_U + a];
+        r.D[a] = V[V_D + a];
+        if (r.D[a] > 0.0) {
+            jlo = fmax(jlo, (-1.0 - r.p[a]) * V[V_INVD + a]);
+            jhi = fmin(jhi, (N[a] - r.p[a]) * V[V_INVD + a]);
+        } else if (r.D[a] < 0.0) {
+            jlo = fmax(jlo, (N[a] - r.p[a]) * V[V_INVD + a]);
+            jhi = fmin(jhi, (-1.0 - r.p[a]) * V[V_INVD + a]);
+        } else if (r.p[a] <= -1.0 || r.p[a] >= N[a]) {
+            empty = true;
+        }
+        r.sg[a] = (r.D[a] < 0.0) ? -1 : 1;
+        r.st[a] = r.sg[a] * ust[a];
+    }
+    jlo = fmin(fmax(jlo, 0.0), V[V_N]);
+    jhi = fmin(fmax(jhi, -1.0), V[V_N]);
+    r.j0 = (int)ceil(jlo);
+    r.j1 = (int)floor(jhi) + 1;
+    if (r.j1 > (int)V[V_N]) r.j1 = (int)V[V_N];
+    if (empty) r.j1 = r.j0;
+    r.stepoff = (int)floor(fabs(r.D[0])) * r.st[0] + (int)floor(fabs(r.D[1])) * r.st[1];
+}
+
+struct f4 { float x, y, z, w; };
+
+TOMO_HD f4 sep_ld4(const float* p)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    f4 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; r.w = p[3]; return r;
+#endif
+}
+
+// S[ix, zq .. zq+3] for padded planes zq .. zq+3 (zq a multiple of 4)
+TOMO_HD void sep_march_xy(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                          const SepSetup& r, int zq, float S[4])
+{
+    const int ust[2] = {dm.sxp, dm.syp};
+    float df[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) { const double ad = fabs(r.D[a]); df[a] = (float)(ad - floor(ad)); }
+    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1];
+    f2 a01 = f2_make(0.f, 0.f), a23 = f2_make(0.f, 0.f);
+    for (int jc = r.j0; jc < r.j1; jc += RAY_REBASE) {
+        float f[2];
+        int off = zq;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const double q = (double)r.sg[a] * (r.p[a] + (double)jc * r.D[a]);
+            const double qi = floor(q);
+            f[a] = (float)(q - qi);
+            int i = (int)qi;
+            if (f[a] >= 1.0f) { f[a] -= 1.0f; i += 1; }
+            off += (TOMO_PAD + r.sg[a] * i) * ust[a];
+        }
+        const int jend = (jc + RAY_REBASE < r.j1) ? jc + RAY_REBASE : r.j1;
+        for (int j = jc; j < jend; ++j) {
+            const float* __restrict__ c = vol + off;
+            const f4 v00 = sep_ld4(c), v01 = sep_ld4(c + o01), v10 = sep_ld4(c + o10), v11 = sep_ld4(c + o11);
+            // bilinear weights of the four (x, y) corners: (1-fx)(1-fy), (1-fx)fy, fx(1-fy), fx fy
+            const float w11 = f[0] * f[1], w10 = f[0] - w11, w01 = f[1] - w11, w00 = (1.0f - f[0]) - w01;
+            a01 = f2_fma(f2_make(w00, w00), f2_make(v00.x, v00.y), a01); a23 = f2_fma(f2_make(w00, w00), f2_make(v00.z, v00.w), a23);
+            a01 = f2_fma(f2_make(w01, w01), f2_make(v01.x, v01.y), a01); a23 = f2_fma(f2_make(w01, w01), f2_make(v01.z, v01.w), a23);
+            a01 = f2_fma(f2_make(w10, w10), f2_make(v10.x, v10.y), a01); a23 = f2_fma(f2_make(w10, w10), f2_make(v10.z, v10.w), a23);
+            a01 = f2_fma(f2_make(w11, w11), f2_make(v11.x, v11.y), a01); a23 = f2_fma(f2_make(w11, w11), f2_make(v11.z, v11.w), a23);
+            f[0] += df[0]; f[1] += df[1];
+            off += r.stepoff;
+            if (f[0] >= 1.0f) { f[0] -= 1.0f; off += r.st[0]; }
+            if (f[1] >= 1.0f) { f[1] -= 1.0f; off += r.st[1]; }
+        }
+    }
+    S[0] = a01.x; S[1] = a01.y; S[2] = a23.x; S[3] = a23.y;
+}
+
+// z cell (padded plane index of the floor corner) and ceil weight of detector row iz
+TOMO_HD void sep_zcell(const double* __restrict__ V, int iz, int& fzp, float& wz)
+{
+    const double zs = V[V_P00 + 2] + (double)iz * V[V_W + 2];
+    const double fl = floor(zs);
+    wz = (float)(zs - fl);
+    fzp = (int)fmin(fmax(fl, -1.0e6), 1.0e6) + TOMO_PAD;
+}

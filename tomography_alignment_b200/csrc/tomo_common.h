@@ -31,7 +31,9 @@ enum {
     V_SPL  = 96,   // 48  voxel-driven derivative_rigid (voxel_utilities.py:23-48): [k][c][4], k = sx,sy,sz,theta,alpha,beta,
                    //     c = 0 (x' row) / 1 (z' row): value = v[0]*cx + v[1]*cy + v[2]*cz + v[3] at voxel centre (cx,cy,cz)
     V_SORG = 144,  // 2   vox_origin - cor_shift, x and z components (voxel_utilities.py:61,90)
-    V_END  = 146
+    V_SEP  = 146,  // 1   1.0 when the view has no tilt (alpha = beta = 0 exactly): W_x = W_y = U_z = D_z = 0, so z decouples
+                   //     from (x, y) and the separable kernels apply
+    V_END  = 147
 };
 
 static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");

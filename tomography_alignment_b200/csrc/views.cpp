@@ -162,6 +162,9 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
             o[V_NCOL] = ncol;
         }
 
+        // untilted view: the z coordinate of a sample depends on iz only and (x, y) on (ix, j) only
+        o[V_SEP] = (W.v[0] == 0.0 && W.v[1] == 0.0 && U.v[2] == 0.0 && D.v[2] == 0.0 && W.v[2] > 0.0) ? 1.0 : 0.0;
+
         // voxel-driven (inverse convention) transform  Ry (Rx Rz x + t)   (external_back_projection.f90:17-25)
         const M3 Vr = mul(Rb, mul(Ra, Rp));
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[V_VROT + 3 * i + j] = Vr.m[i][j];
