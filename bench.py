@@ -321,6 +321,19 @@ def run_b200(a):
                 "per_kernel_algorithmic_gbs": {k: v[1] / (v[0] * 1e-3) / 1e9 for k, v in kernels.items()},
                 "step_frac_of_peak": (bytes_f + bytes_b + bytes_g) * world / (ms_per_step * 1e-3) / 1e9 / peak / world}
 
+    # secondary measurement: the same three kernels on UNTILTED poses (alpha = beta = 0, the default of
+    # projection_matrix and every known-geometry reconstruction), where forward and adjoint take the separable kernels
+    flat = est[mine].copy()
+    flat[:, 1:3] = 0.0
+    be.set_poses(flat)
+    u_f, u_b, u_g = time_kernel(k_fwd), time_kernel(lambda: be.adjoint(meas, out=bp)), time_kernel(k_grad)
+    be.set_poses(est[mine])
+    untilted = {"per_kernel_ms": {"sep_forward_kernel": u_f, "sep_adjoint_kernel(+zgather)": u_b, "ray_kernel_gradient": u_g},
+                "forward_frac_of_peak": bytes_f / (u_f * 1e-3) / 1e9 / peak,
+                "adjoint_frac_of_peak": bytes_b / (u_b * 1e-3) / 1e9 / peak,
+                "step_ms": u_f + u_b + u_g}
+    log("untilted-pose timing done")
+
     # end to end through the public API with pinned host buffers
     e2e = None
     if not a.no_e2e:
@@ -377,7 +390,7 @@ def run_b200(a):
                            "l2": "inputs exceed L2 (volume %d MiB, projections %d MiB per rank)"
                                  % (4 * n ** 3 // 2 ** 20, 4 * my_n * n * n // 2 ** 20),
                            "phantom": "shepp3d", "poses": "examples/generate_data.py jitter, seed 20240229"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "untilted_poses": untilted, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "impl": "b200"}
         print(json.dumps(line))
     if world > 1:

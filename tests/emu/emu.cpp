@@ -85,7 +85,16 @@ EMU_API void emu_back(const TomoGeom* g, const double* views, int n_proj, const 
                 acc += voxel_bilinear_view(proj + v * n_det, V, g->ndx, g->ndz, origin,
                                            g->vox_origin[0] + x * g->vox_pix[0], g->vox_origin[1] + y * g->vox_pix[1],
                                            g->vox_origin[2] + z * g->vox_pix[2]);
-            else
+            else if (V[V_SEP] != 0.0) {
+                // untilted view: separable cores (sep_core.h): K per candidate ix times the z-gathered projection row
+                SepColumn c;
+                sep_column_setup(V, g->ndx, x, y, c);
+                for (int mi = c.milo; mi <= c.mihi; ++mi) {
+                    const float K = sep_column_weight(V, c, mi);
+                    if (K != 0.f)
+                        acc = fmaf(K, sep_zgather(proj + v * n_det + (size_t)(c.n0i + mi) * g->ndz, V, g->ndz, z), acc);
+                }
+            } else
                 acc += adjoint_gather_view(proj + v * n_det, V, g->ndx, g->ndz, x, y, z);
         }
         const size_t vi = ((size_t)x * g->ny + y) * g->nz + z;

@@ -87,6 +87,8 @@ def test_separable_forward_for_untilted_views(shape, dshape, kw):
     assert np.all(be.views[:, 146] == 1.0)                 # V_SEP set by tomo_views_compute_host
     vol = np.random.default_rng(8).random(shape).astype(np.float32)
     assert rel_l2(be.forward(vol).numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    y = np.random.default_rng(9).random((n_proj, og.n_det)).astype(np.float32)
+    assert rel_l2(be.adjoint(y).numpy(), op.adjoint(y)) <= TOL_PROJ             # separable adjoint cores
     # a tilted table is not flagged
     g2, og2, be2, op2, _ = setup(shape, dshape, 3, tilt=0.01)
     assert np.all(be2.views[:, 146] == 0.0)

@@ -348,13 +348,23 @@ def test_separable_forward_for_untilted_views(shape, dshape, kw):
     assert bool((be.views[:, 146] == 1.0).all())
     vol = np.random.default_rng(8).random(shape).astype(np.float32)
     assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    y = np.random.default_rng(9).random((n_proj, og.n_det)).astype(np.float32)
+    refb = op.adjoint(y)
+    gotb = be.adjoint(torch.as_tensor(y))
+    assert rel_l2(gotb.cpu().numpy(), refb) <= TOL_PROJ                         # sep_zgather + sep_adjoint kernels
+    assert rel_l2(be.adjoint(torch.as_tensor(y), gather=True).cpu().numpy(), refb) <= TOL_PROJ
+    assert torch.equal(be.adjoint(torch.as_tensor(y)), gotb)                     # bitwise reproducible
+    base = torch.full(tuple(shape), 0.25, dtype=torch.float32, device="cuda")
+    be.adjoint(torch.as_tensor(y), out=base, accumulate=True)
+    assert rel_l2(base.cpu().numpy().ravel() - 0.25, refb) <= 2e-5
     # mixed table: views 1, 4 tilted
     phi, alpha, beta, xyz = random_poses(n_proj, 3, tilt=0.0, phis=phis)
     alpha[[1, 4]] = [0.01, -0.02]
     be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
     assert be.views[:, 146].cpu().tolist() == [1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0]
-    ref = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz).forward(vol)
-    assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), ref) <= TOL_PROJ
+    mixed = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), mixed.forward(vol)) <= TOL_PROJ
+    assert rel_l2(be.adjoint(torch.as_tensor(y)).cpu().numpy(), mixed.adjoint(y)) <= TOL_PROJ
 
 
 def test_error_codes_surface_as_exceptions():

@@ -60,6 +60,10 @@ def load():
     L.tomo_forward.argtypes = [G, vp, ci, vp, vp, vp]
     L.tomo_back_adjoint.restype = ci
     L.tomo_back_adjoint.argtypes = [G, vp, ci, vp, vp, ci, vp]
+    L.tomo_back_adjoint_workspace_bytes.restype = sz
+    L.tomo_back_adjoint_workspace_bytes.argtypes = [G, ci]
+    L.tomo_back_adjoint_ws.restype = ci
+    L.tomo_back_adjoint_ws.argtypes = [G, vp, ci, vp, vp, ci, vp, sz, vp]
     L.tomo_back_adjoint_gather.restype = ci
     L.tomo_back_adjoint_gather.argtypes = [G, vp, ci, vp, vp, ci, vp]
     L.tomo_back_voxel_bilinear.restype = ci

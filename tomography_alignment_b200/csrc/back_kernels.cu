@@ -45,6 +45,7 @@ struct BackArgs {
     float*        vol;       // [nx][ny][nz]
     int nx, ny, nz, ndx, ndz, n_proj, accumulate;
     int only_uncoloured;     // gather kernel: visit only the views the tile kernel skipped (V_NCOL == 0)
+    int skip_separable;      // leave views with V_SEP == 1 to the separable adjoint (workspace variant)
     double origin[3];        // voxel_bilinear only: the Fortran's origin argument
     double vox0[3], vpix[3]; // voxel_bilinear only: physical voxel centres = vox0 + idx*vpix
 };
@@ -62,6 +63,7 @@ adjoint_gather_kernel(const BackArgs A)
     for (int view = 0; view < A.n_proj; ++view) {
         const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
         if (A.only_uncoloured && V[V_NCOL] != 0.0) continue;
+        if (A.skip_separable && V[V_SEP] != 0.0) continue;
         acc += adjoint_gather_view(A.proj + (size_t)view * n_det, V, A.ndx, A.ndz, x, y, z);
     }
     const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
@@ -247,8 +249,10 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     for (int view = 0; view < A.n_proj; ++view) {
         const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
         TileView tv;
+        const double vsep = V[V_SEP];                    // both flags loaded before the first branch
         tv.ncol = (int)V[V_NCOL];
         if (tv.ncol == 0) continue;                      // outside the scatter envelope: the gather kernel adds it
+        if (A.skip_separable && vsep != 0.0) continue;   // untilted view: the separable adjoint adds it
         // lattice coordinates of the active box: centre +- sum |Linv| * half widths (exact for a linear map)
         double B[3], cc[3];
 #pragma unroll
@@ -370,7 +374,7 @@ static int fill_back(const TomoGeom* g, const void* views, int n_proj, const flo
     if (!g || !views || !proj || !vol || n_proj <= 0) { tomo_set_error("backprojector: null pointer or n_proj <= 0"); return TOMO_E_ARG; }
     A->proj = proj; A->views = (const double*)views; A->vol = vol;
     A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz;
-    A->n_proj = n_proj; A->accumulate = accumulate; A->only_uncoloured = 0;
+    A->n_proj = n_proj; A->accumulate = accumulate; A->only_uncoloured = 0; A->skip_separable = 0;
     for (int a = 0; a < 3; ++a) { A->origin[a] = 0.0; A->vox0[a] = g->vox_origin[a]; A->vpix[a] = g->vox_pix[a]; }
     *grid = dim3((g->nz + BZ - 1) / BZ, (g->ny + BY - 1) / BY, (g->nx + BX - 1) / BX);
     if (grid->y > 65535u || grid->z > 65535u) { tomo_set_error("backprojector: volume too large for the launch grid"); return TOMO_E_RANGE; }
@@ -386,11 +390,27 @@ extern "C" int tomo_back_adjoint_gather(const TomoGeom* g, const void* views, in
     return tomo_check_cuda(cudaGetLastError(), "adjoint_gather_kernel");
 }
 
-extern "C" int tomo_back_adjoint(const TomoGeom* g, const void* views, int n_proj,
-                                 const float* proj, float* vol, int accumulate, void* stream)
+size_t tomo_back_separable_workspace_bytes(const TomoGeom* g, int n_proj);
+int tomo_back_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
+                               int accumulate, void* workspace, void* stream);
+
+extern "C" size_t tomo_back_adjoint_workspace_bytes(const TomoGeom* g, int n_proj)
+{
+    if (!g || n_proj <= 0) return 0;
+    return tomo_back_separable_workspace_bytes(g, n_proj);
+}
+
+static int back_adjoint_impl(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
+                             int accumulate, void* workspace, size_t workspace_bytes, void* stream)
 {
     BackArgs A; dim3 grid;
     if (int e = fill_back(g, views, n_proj, proj, vol, accumulate, &A, &grid)) return e;
+    const bool sep = workspace != nullptr;
+    if (sep && workspace_bytes < tomo_back_separable_workspace_bytes(g, n_proj)) {
+        tomo_set_error("tomo_back_adjoint_ws: workspace too small (see tomo_back_adjoint_workspace_bytes)");
+        return TOMO_E_WORKSPACE;
+    }
+    A.skip_separable = sep ? 1 : 0;
     constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
     const int ntx = (g->nx + TX - 1) / TX, nty = (g->ny + TY - 1) / TY, ntz = (g->nz + TZ - 1) / TZ;
     const size_t smem = sizeof(float) * TSMEM_FLOATS;
@@ -404,7 +424,23 @@ extern "C" int tomo_back_adjoint(const TomoGeom* g, const void* views, int n_pro
     // gather kernel adds them; it returns at once when record 0 says there are none
     A.only_uncoloured = 1; A.accumulate = 1;
     adjoint_gather_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A);
-    return tomo_check_cuda(cudaGetLastError(), "adjoint_gather_kernel(uncoloured)");
+    if (int e = tomo_check_cuda(cudaGetLastError(), "adjoint_gather_kernel(uncoloured)")) return e;
+    // untilted views: separable adjoint (needs the Yz workspace); it returns at once for tilted views
+    if (sep) return tomo_back_separable_launch(g, views, n_proj, proj, vol, 1, workspace, stream);
+    return 0;
+}
+
+extern "C" int tomo_back_adjoint(const TomoGeom* g, const void* views, int n_proj,
+                                 const float* proj, float* vol, int accumulate, void* stream)
+{
+    return back_adjoint_impl(g, views, n_proj, proj, vol, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int tomo_back_adjoint_ws(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
+                                    int accumulate, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!workspace) { tomo_set_error("tomo_back_adjoint_ws: workspace is NULL"); return TOMO_E_ARG; }
+    return back_adjoint_impl(g, views, n_proj, proj, vol, accumulate, workspace, workspace_bytes, stream);
 }
 
 extern "C" int tomo_back_voxel_bilinear(const TomoGeom* g, const void* views, int n_proj,

@@ -11,6 +11,8 @@
 #pragma once
 #include "ray_core.h"
 
+TOMO_HD float tomo_tent_f(float d) { return fmaxf(0.f, 1.f - fabsf(d)); }
+
 #define SEP_CHUNK 128                    // z planes staged per warp
 #define SEP_OUT   (SEP_CHUNK - 4)        // planes a chunk produces outputs for (needs S[z] and S[z+1])
 
@@ -112,4 +114,62 @@ TOMO_HD void sep_zcell(const double* __restrict__ V, int iz, int& fzp, float& wz
     const double fl = floor(zs);
     wz = (float)(zs - fl);
     fzp = (int)fmin(fmax(fl, -1.0e6), 1.0e6) + TOMO_PAD;
+}
+
+// ---- separable adjoint (untilted views) -----------------------------------------------------------------------
+// vol[x, y, z] += sum_ix K(ix; x, y) * Yz[ix, z]   with
+//   Yz[ix, z]    = sum_iz tent(z0 + iz W_z - z) * y[ix, iz]          (transpose of the 2-tap z interpolation)
+//   K(ix; x, y)  = sum_j tent(x_j - x) tent(y_j - y)                 (transpose of the bilinear (x, y) part)
+// -- the same terms as the generic adjoint (back_core.h), regrouped; exact because z decouples when W = (0,0,W_z).
+
+// Yz[ix, z] for one voxel plane z: the (at most 3 for W_z > 2/3) detector rows within one voxel of it
+TOMO_HD float sep_zgather(const float* __restrict__ Prow, const double* __restrict__ V, int ndz, int z)
+{
+    const double z0 = V[V_P00 + 2], wz = V[V_W + 2];
+    const double lo = ((double)z - 1.0 - z0) / wz, hi = ((double)z + 1.0 - z0) / wz;
+    int i0 = (int)fmin(fmax(ceil(lo), 0.0), (double)ndz), i1 = (int)fmin(fmax(floor(hi), -1.0), (double)(ndz - 1));
+    float acc = 0.f;
+    for (int iz = i0; iz <= i1; ++iz) {
+        const float d = (float)(z0 + (double)iz * wz - (double)z);
+        acc = fmaf(tomo_tent_f(d), TOMO_LDG(Prow + iz), acc);
+    }
+    return acc;
+}
+
+// Candidate ix range and the in-plane lattice coordinates of voxel column (x, y)
+struct SepColumn {
+    int n0i, n0j, milo, mihi, mjlo, mjhi;
+    float rhoi, rhoj;
+};
+
+TOMO_HD void sep_column_setup(const double* __restrict__ V, int ndx, int x, int y, SepColumn& c)
+{
+    const double vx = (double)x - V[V_P00 + 0], vy = (double)y - V[V_P00 + 1];
+    const double qi = V[V_LINV + 0] * vx + V[V_LINV + 1] * vy;          // lattice ix of the column
+    const double qj = V[V_LINV + 6] * vx + V[V_LINV + 7] * vy;          // lattice j
+    const double ri = rint(fmin(fmax(qi, -1.0e9), 1.0e9)), rj = rint(fmin(fmax(qj, -1.0e9), 1.0e9));
+    c.n0i = (int)ri; c.n0j = (int)rj;
+    c.rhoi = (float)(qi - ri); c.rhoj = (float)(qj - rj);
+    const float rbi = (float)(fabs(V[V_LINV + 0]) + fabs(V[V_LINV + 1])) * 1.0001f + 1e-4f;
+    const float rbj = (float)(fabs(V[V_LINV + 6]) + fabs(V[V_LINV + 7])) * 1.0001f + 1e-4f;
+    c.milo = (int)ceilf(c.rhoi - rbi); c.mihi = (int)floorf(c.rhoi + rbi);
+    c.mjlo = (int)ceilf(c.rhoj - rbj); c.mjhi = (int)floorf(c.rhoj + rbj);
+    const int nj = (int)V[V_N];
+    if (c.milo < -c.n0i) c.milo = -c.n0i;
+    if (c.mihi > ndx - 1 - c.n0i) c.mihi = ndx - 1 - c.n0i;
+    if (c.mjlo < -c.n0j) c.mjlo = -c.n0j;
+    if (c.mjhi > nj - 1 - c.n0j) c.mjhi = nj - 1 - c.n0j;
+}
+
+// K(ix = n0i + mi; x, y)
+TOMO_HD float sep_column_weight(const double* __restrict__ V, const SepColumn& c, int mi)
+{
+    const float Ux = (float)V[V_U], Uy = (float)V[V_U + 1], Dx = (float)V[V_D], Dy = (float)V[V_D + 1];
+    const float ci = (float)mi - c.rhoi;
+    float K = 0.f;
+    for (int mj = c.mjlo; mj <= c.mjhi; ++mj) {
+        const float cj = (float)mj - c.rhoj;
+        K = fmaf(tomo_tent_f(fmaf(ci, Ux, cj * Dx)), tomo_tent_f(fmaf(ci, Uy, cj * Dy)), K);
+    }
+    return K;
 }

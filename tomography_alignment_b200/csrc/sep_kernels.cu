@@ -25,13 +25,16 @@ __global__ void __launch_bounds__(32 * SEP_WARPS)
 sep_forward_kernel(const SepArgs A)
 {
     __shared__ float Srow[SEP_WARPS][SEP_CHUNK];
-    int bid = blockIdx.x;
-    const int xt = bid % A.nxt; bid /= A.nxt;
-    const int view = bid % A.n_proj;
-    const int chunk = bid / A.n_proj;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    // one block per (chunk, view, x-tile) item (a persistent grid-stride loop measured 25 % slower); blocks of
+    // tilted views return at once
+    {
+    const long long item = blockIdx.x;
+    const int xt = (int)(item % A.nxt);
+    const int view = (int)((item / A.nxt) % A.n_proj);
+    const int chunk = (int)(item / ((long long)A.nxt * A.n_proj));
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
     if (V[V_SEP] == 0.0) return;                                   // tilted view: the generic kernel does it
-    const int lane = threadIdx.x, warp = threadIdx.y;
     const int ix = xt * SEP_WARPS + warp;
     if (ix >= A.ndx) return;                                       // whole warp
     const RayDims dm = {A.nx, A.ny, A.nz, A.sxp, A.syp};
@@ -65,6 +68,85 @@ sep_forward_kernel(const SepArgs A)
         }
         out[iz] = v;
     }
+    }
+}
+
+// ---- separable adjoint ------------------------------------------------------------------------------------------
+constexpr int SA_WARPS_X = 4, SA_WARPS_Y = 4;        // a block = 4 x 4 voxel columns, one warp each
+constexpr int SA_QPL = 4;                            // z quads per lane: a warp covers 32 * 4 * 4 = 512 planes
+
+struct SepBackArgs {
+    const float*  proj;      // [n_proj][ndx][ndz]
+    const double* views;
+    float*        yz;        // workspace [n_proj][ndx][nzw]
+    float*        vol;
+    int nx, ny, nz, ndx, ndz, n_proj, nzw, accumulate;
+};
+
+// Yz[view][ix][z] (z-transpose of the 2-tap interpolation) for the separable views of the table
+__global__ void __launch_bounds__(256)
+sep_zgather_kernel(const SepBackArgs A)
+{
+    if (A.views[V_NSEP] == 0.0) return;                               // no untilted view in the table
+    const long long nrows = (long long)A.n_proj * A.ndx;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int view = (int)(row / A.ndx), ix = (int)(row % A.ndx);
+        const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+        if (V[V_SEP] == 0.0) continue;
+        const float* __restrict__ Prow = A.proj + ((size_t)view * A.ndx + ix) * A.ndz;
+        for (int z = threadIdx.x; z < A.nzw; z += 256)
+            A.yz[((size_t)view * A.ndx + ix) * A.nzw + z] = (z < A.nz) ? sep_zgather(Prow, V, A.ndz, z) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(32 * SA_WARPS_X * SA_WARPS_Y)
+sep_adjoint_kernel(const SepBackArgs A)
+{
+    const int lane = threadIdx.x;
+    if (A.views[V_NSEP] == 0.0) return;                               // no untilted view in the table
+    const int x = blockIdx.y * SA_WARPS_X + threadIdx.z, y = blockIdx.x * SA_WARPS_Y + threadIdx.y;
+    if (x >= A.nx || y >= A.ny) return;                               // whole warp
+    const int zbase = blockIdx.z * (128 * SA_QPL);
+    f2 acc[SA_QPL][2];
+#pragma unroll
+    for (int q = 0; q < SA_QPL; ++q) { acc[q][0] = f2_make(0.f, 0.f); acc[q][1] = f2_make(0.f, 0.f); }
+    for (int view = 0; view < A.n_proj; ++view) {
+        const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+        if (V[V_SEP] == 0.0) continue;
+        SepColumn c;
+        sep_column_setup(V, A.ndx, x, y, c);                           // warp-uniform
+        // lane k evaluates K for candidate ix number k, then the values are broadcast one by one
+        const int nmi = c.mihi - c.milo + 1;
+        for (int m0 = 0; m0 < nmi; m0 += 32) {
+            const int mine = c.milo + m0 + lane;
+            const float Kl = (mine <= c.mihi) ? sep_column_weight(V, c, mine) : 0.f;
+            const int cnt = min(32, nmi - m0);
+            for (int k = 0; k < cnt; ++k) {
+                const float K = __shfl_sync(0xffffffffu, Kl, k);
+                if (K == 0.f) continue;                                // warp-uniform
+                const int ix = c.n0i + c.milo + m0 + k;
+                const float* __restrict__ row = A.yz + ((size_t)view * A.ndx + ix) * A.nzw + zbase + 4 * lane;
+                const f2 K2 = f2_make(K, K);
+#pragma unroll
+                for (int q = 0; q < SA_QPL; ++q) {
+                    if (zbase + 128 * q + 4 * lane < A.nzw) {
+                        const f4 v = sep_ld4(row + 128 * q);
+                        acc[q][0] = f2_fma(K2, f2_make(v.x, v.y), acc[q][0]);
+                        acc[q][1] = f2_fma(K2, f2_make(v.z, v.w), acc[q][1]);
+                    }
+                }
+            }
+        }
+    }
+    float* __restrict__ out = A.vol + ((size_t)x * A.ny + y) * A.nz;
+#pragma unroll
+    for (int q = 0; q < SA_QPL; ++q) {
+        const int z = zbase + 128 * q + 4 * lane;
+        const float r[4] = {acc[q][0].x, acc[q][0].y, acc[q][1].x, acc[q][1].y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (z + k < A.nz) out[z + k] = A.accumulate ? out[z + k] + r[k] : r[k];
+    }
 }
 
 }  // namespace
@@ -90,4 +172,29 @@ int tomo_forward_separable_launch(const TomoGeom* g, const void* views, int n_pr
     if (nblocks >= 2147483647.0) { tomo_set_error("separable forward: too many blocks for one launch"); return TOMO_E_RANGE; }
     sep_forward_kernel<<<(unsigned)nblocks, dim3(32, SEP_WARPS), 0, (cudaStream_t)stream>>>(A);
     return tomo_check_cuda(cudaGetLastError(), "sep_forward_kernel");
+}
+
+// Workspace (floats) the separable adjoint needs: Yz for every view of the table
+size_t tomo_back_separable_workspace_bytes(const TomoGeom* g, int n_proj)
+{
+    return sizeof(float) * (size_t)n_proj * g->ndx * (size_t)(((g->nz + 3) / 4) * 4);
+}
+
+// vol (+)= A^T y restricted to the separable views of the table (the caller has already handled the others)
+int tomo_back_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
+                               int accumulate, void* workspace, void* stream)
+{
+    SepBackArgs A;
+    A.proj = proj; A.views = (const double*)views; A.yz = (float*)workspace; A.vol = vol;
+    A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
+    A.nzw = ((g->nz + 3) / 4) * 4;
+    A.accumulate = accumulate;
+    const double nrows = (double)g->ndx * n_proj;
+    sep_zgather_kernel<<<(unsigned)(nrows < 148.0 * 32 ? nrows : 148.0 * 32), 256, 0, (cudaStream_t)stream>>>(A);
+    if (int e = tomo_check_cuda(cudaGetLastError(), "sep_zgather_kernel")) return e;
+    const dim3 grid((g->ny + SA_WARPS_Y - 1) / SA_WARPS_Y, (g->nx + SA_WARPS_X - 1) / SA_WARPS_X,
+                    (A.nzw + 128 * SA_QPL - 1) / (128 * SA_QPL));
+    if (grid.y > 65535u || grid.z > 65535u) { tomo_set_error("separable adjoint: volume too large for the launch grid"); return TOMO_E_RANGE; }
+    sep_adjoint_kernel<<<grid, dim3(32, SA_WARPS_Y, SA_WARPS_X), 0, (cudaStream_t)stream>>>(A);
+    return tomo_check_cuda(cudaGetLastError(), "sep_adjoint_kernel");
 }

@@ -33,7 +33,8 @@ enum {
     V_SORG = 144,  // 2   vox_origin - cor_shift, x and z components (voxel_utilities.py:61,90)
     V_SEP  = 146,  // 1   1.0 when the view has no tilt (alpha = beta = 0 exactly): W_x = W_y = U_z = D_z = 0, so z decouples
                    //     from (x, y) and the separable kernels apply
-    V_END  = 147
+    V_NSEP = 147,  // 1   number of views of the whole table with V_SEP == 1 (same in every record)
+    V_END  = 148
 };
 
 static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");

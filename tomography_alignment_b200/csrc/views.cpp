@@ -192,6 +192,11 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
     }
     double n_uncoloured = 0.0;
     for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_NCOL] == 0.0) n_uncoloured += 1.0;
-    for (int v = 0; v < n_proj; ++v) out[(size_t)v * TOMO_VIEW_STRIDE + V_NUNCOL] = n_uncoloured;
+    double n_sep = 0.0;
+    for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_SEP] != 0.0) n_sep += 1.0;
+    for (int v = 0; v < n_proj; ++v) {
+        out[(size_t)v * TOMO_VIEW_STRIDE + V_NUNCOL] = n_uncoloured;
+        out[(size_t)v * TOMO_VIEW_STRIDE + V_NSEP] = n_sep;
+    }
     return 0;
 }

@@ -78,6 +78,15 @@ class CudaBackend(object):
             self._dbuf[name] = t
         return t
 
+    def _back_ws(self, n_views):
+        """Workspace of the separable adjoint (z-transposed projections of the untilted views)."""
+        nbytes = self.lib.tomo_back_adjoint_workspace_bytes(self._g(), n_views)
+        t = self._dbuf.get("back_ws")
+        if t is None or t.numel() * 4 < nbytes:
+            t = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            self._dbuf["back_ws"] = t
+        return t, nbytes
+
     def _copy_stream(self):
         if self._copy is None:
             self._copy = torch.cuda.Stream(device=self.device)
@@ -139,9 +148,14 @@ class CudaBackend(object):
         if out is None:
             out = torch.empty(self.vol_shape, dtype=torch.float32, device=self.device)
             accumulate = False
-        fn = self.lib.tomo_back_adjoint_gather if gather else self.lib.tomo_back_adjoint
         with torch.cuda.device(self.device):
-            rc = fn(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out), int(bool(accumulate)), self._stream())
+            if gather:
+                rc = self.lib.tomo_back_adjoint_gather(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out),
+                                                       int(bool(accumulate)), self._stream())
+            else:
+                ws, nbytes = self._back_ws(self.n_proj)
+                rc = self.lib.tomo_back_adjoint_ws(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out),
+                                                   int(bool(accumulate)), _ptr(ws), nbytes, self._stream())
         _lib.check(rc, "tomo_back_adjoint")
         self.launches += 1
         return out
@@ -191,6 +205,7 @@ class CudaBackend(object):
         y_d = self._buf("proj", (self.n_proj,) + self.det_shape).reshape(self.n_proj, -1)
         vol_d = self._buf("vol", self.vol_shape)
         chunks = self._chunks(chunk_views)
+        ws, ws_bytes = self._back_ws(max(b - a for a, b in chunks))
         cp.wait_stream(cur)                      # y_d / vol_d may still be in use by earlier work on `cur`
         evs = []
         with torch.cuda.stream(cp):
@@ -202,8 +217,8 @@ class CudaBackend(object):
         with torch.cuda.device(self.device):
             for k, (a, b) in enumerate(chunks):
                 cur.wait_event(evs[k])
-                rc = self.lib.tomo_back_adjoint(self._g(), self._views_at(a), b - a, _ptr(y_d[a:b]), _ptr(vol_d),
-                                                int(k > 0), self._stream())
+                rc = self.lib.tomo_back_adjoint_ws(self._g(), self._views_at(a), b - a, _ptr(y_d[a:b]), _ptr(vol_d),
+                                                   int(k > 0), _ptr(ws), ws_bytes, self._stream())
                 _lib.check(rc, "tomo_back_adjoint")
                 self.launches += 2
         out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
