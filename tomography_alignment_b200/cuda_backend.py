@@ -138,7 +138,7 @@ class CudaBackend(object):
         with torch.cuda.device(self.device):
             rc = self.lib.tomo_forward(self._g(), _ptr(self.views), self.n_proj, _ptr(volpad), _ptr(out), self._stream())
         _lib.check(rc, "tomo_forward")
-        self.launches += 1
+        self.launches += 2       # ray_kernel_forward + sep_forward_kernel (each skips the other's views)
         return out
 
     def adjoint(self, y, out=None, accumulate=False, gather=False):
@@ -157,7 +157,7 @@ class CudaBackend(object):
                 rc = self.lib.tomo_back_adjoint_ws(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out),
                                                    int(bool(accumulate)), _ptr(ws), nbytes, self._stream())
         _lib.check(rc, "tomo_back_adjoint")
-        self.launches += 1
+        self.launches += 1 if gather else 4   # tile + gather(uncoloured) + sep_zgather + sep_adjoint
         return out
 
     # -- host-buffer entry points: copies overlapped with the kernels in view chunks ------------------
@@ -180,7 +180,7 @@ class CudaBackend(object):
             for a, b in self._chunks(chunk_views):
                 rc = self.lib.tomo_forward(self._g(), self._views_at(a), b - a, _ptr(volpad), _ptr(proj_d[a:b]), self._stream())
                 _lib.check(rc, "tomo_forward")
-                self.launches += 1
+                self.launches += 2
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 with torch.cuda.stream(cp):
@@ -220,7 +220,7 @@ class CudaBackend(object):
                 rc = self.lib.tomo_back_adjoint_ws(self._g(), self._views_at(a), b - a, _ptr(y_d[a:b]), _ptr(vol_d),
                                                    int(k > 0), _ptr(ws), ws_bytes, self._stream())
                 _lib.check(rc, "tomo_back_adjoint")
-                self.launches += 2
+                self.launches += 4
         out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
         cur.synchronize()
         self.h2d_bytes += 4 * y_host.numel()
