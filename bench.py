@@ -168,8 +168,8 @@ class ClockSampler(object):
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
 def run_b200(a):
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner (and warnings) to stdout by default
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from tomography_alignment_b200 import Geometry, ProjectionMatrix, pose_table
@@ -350,11 +350,13 @@ def run_b200(a):
         def e2e_step():
             # host buffers in, host buffers out; copies are issued inside the calls (view chunks, side stream)
             A._backend.forward_host(h_vol, out_host=h_proj)          # H2D volume, forward, D2H projections
-            A._backend.adjoint_host(h_meas, out_host=h_bp)           # H2D projections, adjoint, D2H volume
-            if world > 1:                                            # Allreduce of recon/sirt_mpi.py:103 on host data
-                v = h_bp.to(dev, non_blocking=True)
+            if world == 1:
+                A._backend.adjoint_host(h_meas, out_host=h_bp)       # H2D projections, adjoint, D2H volume
+            else:                                                    # Allreduce of recon/sirt_mpi.py:103 before the D2H
+                v = A._backend.adjoint_host(h_meas, out_host=None, to_host=False)
                 dist.all_reduce(v)
                 h_bp.copy_(v)
+                A._backend.d2h_bytes += 4 * v.numel()
             g6, c = A._backend.proj_grad_host(h_vol, h_meas)         # H2D volume + measured, D2H (n, 6) gradients
             return g6, c
 

@@ -157,6 +157,17 @@ TOMO_API int tomo_proj_grad(const TomoGeom* geom, const void* views_dev, int n_p
                    float* proj_dev, float* dproj_dev, double* grad6_dev, double* cost_dev,
                    void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- TV proximal step ------------------------------------------------------ */
+/* Dual FISTA iteration of utilities/tv_denoise.py:98-170 (denoise_fista), two fused stencil kernels.
+ * Fields p / aux / gim: float32 [3][nx][ny][nz]; im / err: float32 [nx][ny][nz].
+ *   tomo_tv_dual_error : err = weight * div(p) - im                       (tv_denoise.py:147, div :20-31)
+ *   tomo_tv_dual_update: aux += gradient(err) * inv_factor_weight; tmp = aux / max(|aux|, 1);
+ *                        aux = (1 + t_factor) * tmp - t_factor * gim; gim = tmp      (:148-154) */
+TOMO_API int tomo_tv_dual_error(int nx, int ny, int nz, float weight, const float* p_dev, const float* im_dev,
+                       float* err_dev, void* stream);
+TOMO_API int tomo_tv_dual_update(int nx, int ny, int nz, float inv_factor_weight, float t_factor,
+                        const float* err_dev, float* aux_dev, float* gim_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,16 @@ def main():
     from utilities import generate_phantom
     for n in (16, 24):
         out["shepp3d/%d" % n] = generate_phantom.shepp3d(n)
+    # TV proximal step: the reference's tv_denoise.py is pure numpy and runs as is
+    from utilities import tv_denoise
+    tv_im = rng.random((12, 10, 14)).astype(np.float32) + np.linspace(0, 2, 14, dtype=np.float32)[None, None, :]
+    out["tv/im"] = tv_im
+    out["tv/div_in"] = rng.random((3, 12, 10, 14)).astype(np.float32)
+    out["tv/div"] = tv_denoise.div(out["tv/div_in"])
+    out["tv/gradient"] = tv_denoise.gradient(tv_im)
+    for w, nit in ((0.05, 7), (0.5, 20), (2.0, 60)):
+        out["tv/denoise_w%g_n%d" % (w, nit)] = tv_denoise.denoise_fista(tv_im, weight=w, niter=nit)
+    out["tv/tv_norm_3d"] = np.array(tv_denoise.tv_norm_3d(tv_im))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -70,6 +70,10 @@ def load():
     L.tomo_back_voxel_bilinear.argtypes = [G, vp, ci, vp, vp, vp, ci, vp]
     L.tomo_voxel_splat.restype = ci
     L.tomo_voxel_splat.argtypes = [G, vp, ci, vp, vp, vp, vp]
+    L.tomo_tv_dual_error.restype = ci
+    L.tomo_tv_dual_error.argtypes = [ci, ci, ci, ctypes.c_float, vp, vp, vp, vp]
+    L.tomo_tv_dual_update.restype = ci
+    L.tomo_tv_dual_update.argtypes = [ci, ci, ci, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp]
     L.tomo_proj_grad_workspace_bytes.restype = sz
     L.tomo_proj_grad_workspace_bytes.argtypes = [G, ci]
     L.tomo_proj_grad.restype = ci

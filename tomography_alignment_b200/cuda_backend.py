@@ -192,14 +192,15 @@ class CudaBackend(object):
         self.d2h_bytes += 4 * out3.numel()
         return out_host
 
-    def adjoint_host(self, y_host, out_host=None, chunk_views=None):
+    def adjoint_host(self, y_host, out_host=None, chunk_views=None, to_host=True):
         """vol = A^T y with HOST input and output: projection chunks go up on a side stream while the
-        previous chunk is backprojected (accumulating launches), the volume comes down once."""
+        previous chunk is backprojected (accumulating launches), the volume comes down once.
+        ``to_host=False`` returns the device volume instead (callers that all-reduce before the download)."""
         y_host = self._host(y_host)
         if y_host.numel() != self.n_proj * self.n_det:
             raise ValueError("projections have %d elements, operator expects %d" % (y_host.numel(), self.n_proj * self.n_det))
         y_host = y_host.reshape(self.n_proj, -1)
-        if out_host is None:
+        if out_host is None and to_host:
             out_host = torch.empty(self.vol_shape, dtype=torch.float32, pin_memory=True)
         cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
         y_d = self._buf("proj", (self.n_proj,) + self.det_shape).reshape(self.n_proj, -1)
@@ -221,9 +222,11 @@ class CudaBackend(object):
                                                    int(k > 0), _ptr(ws), ws_bytes, self._stream())
                 _lib.check(rc, "tomo_back_adjoint")
                 self.launches += 4
+        self.h2d_bytes += 4 * y_host.numel()
+        if not to_host:
+            return vol_d
         out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
         cur.synchronize()
-        self.h2d_bytes += 4 * y_host.numel()
         self.d2h_bytes += 4 * out_host.numel()
         return out_host
 

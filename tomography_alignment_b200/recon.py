@@ -180,3 +180,51 @@ class CGLS(_DeviceSolver):
                 self.rms_error[k] = float(torch.linalg.vector_norm((self.rec - self.ground_truth).double())) / norm_factor
             k += 1
         return self._result(self.rms_error, k)
+
+
+class RegularizedRecon(_DeviceSolver):
+    """recon/regularized.py:13-154 on the device: FISTA with a TV proximal step (``run_fista``).
+    u_k = prox_{gamma g}(x_{k-1} + gamma A^T (b - A x_{k-1})); x_k = u_k + (t_{k-1} - 1)/t_k (u_k - u_{k-1}), gamma = 1/hyper;
+    the prox is tv_denoise.denoise_fista(weight = gamma * beta_tv, niter = niter_tv) (regularized.py:84-103).
+    With ``group`` the views are sharded and the backprojection all-reduced like recon/regularized_mpi.py:110-116;
+    every rank then applies the (deterministic) prox redundantly, so no broadcast is needed (:118-137)."""
+
+    def __init__(self, geometry, projections, angles, xyz_shifts, options=None, group=None, device=None, backend=None,
+                 tv_ops=None):
+        super().__init__(geometry, projections, angles, xyz_shifts, options, group, device, backend)
+        self.tv_ops = tv_ops
+        self.norm_factor = self._norm_factor()
+
+    def run_fista(self, niter=100, make_plot=False, hyper=1.e4, beta_tv=1.0, niter_tv=20):
+        from . import tv_denoise
+        shape = tuple(int(v) for v in self.geometry.vox_shape)
+        gamma = 1. / hyper
+        t = 1.0
+        rms_error = np.zeros(niter, )
+        self.total_cost = np.zeros(niter, )
+        self.data_fidelity_cost = np.zeros(niter, )
+        u_old = self.rec.clone()
+        k, stop = 0, 0
+        while k < niter and not stop:
+            res = self.projections - self._A(self.rec)
+            back_proj = self._At(res)
+            x_tmp = self.rec + gamma * back_proj
+            u = tv_denoise.denoise_fista(x_tmp.reshape(shape), weight=gamma * beta_tv, niter=niter_tv, ops=self.tv_ops)
+            t_old = t
+            t = 0.5 * (1.0 + np.sqrt(1 + 4 * t_old ** 2))
+            u = torch.as_tensor(u).to(self.rec.device).reshape(-1)
+            self.rec = u + (t_old - 1) / t * (u - u_old)
+            u_old = u
+            self.data_fidelity_cost[k] = 0.5 * float(self._sum((res.double() ** 2).sum()))
+            tv_value = beta_tv * tv_denoise.tv_norm_3d(self.rec.reshape(shape))
+            self.total_cost[k] = self.data_fidelity_cost[k] + tv_value
+            if self.ground_truth is None:
+                rms_error[k] = np.sqrt(2 * self.data_fidelity_cost[k]) / self.norm_factor
+            else:
+                rms_error[k] = float(torch.linalg.vector_norm((self.ground_truth - self.rec).double())) / self.norm_factor
+            if k > 0 and rms_error[k] > rms_error[k - 1]:
+                stop = 1
+                if self.rank == 0:
+                    print('semi-convergence criterion reached: stopping at k %3d with RMSE = %4.5f' % (k, rms_error[k]))
+            k += 1
+        return self.rec.cpu().numpy().astype(self.precision, copy=False), rms_error[:k]
