@@ -328,9 +328,10 @@ def run_b200(a):
     be.set_poses(flat)
     u_f, u_b, u_g = time_kernel(k_fwd), time_kernel(lambda: be.adjoint(meas, out=bp)), time_kernel(k_grad)
     be.set_poses(est[mine])
-    untilted = {"per_kernel_ms": {"sep_forward_kernel": u_f, "sep_adjoint_kernel(+zgather)": u_b, "ray_kernel_gradient": u_g},
+    untilted = {"per_kernel_ms": {"sep_forward_kernel": u_f, "sep_adjoint_kernel(+zgather)": u_b, "sep_gradient_kernel": u_g},
                 "forward_frac_of_peak": bytes_f / (u_f * 1e-3) / 1e9 / peak,
                 "adjoint_frac_of_peak": bytes_b / (u_b * 1e-3) / 1e9 / peak,
+                "gradient_frac_of_peak": bytes_g / (u_g * 1e-3) / 1e9 / peak,
                 "step_ms": u_f + u_b + u_g}
     log("untilted-pose timing done")
 

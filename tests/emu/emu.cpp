@@ -45,6 +45,44 @@ EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, c
             }
             continue;
         }
+        if (want_grad && V[V_SEP] != 0.0) {
+            // untilted view: separable gradient cores (sep_core.h)
+            const int nzp = tomo_nzp(g->nz);
+#pragma omp parallel for schedule(dynamic, 8)
+            for (int ix = 0; ix < g->ndx; ++ix) {
+                std::vector<float> S(nzp), T(nzp), Gx(nzp), Gy(nzp), TGx(nzp), TGy(nzp);
+                SepSetup r;
+                sep_setup(V, dm, ix, r);
+                for (int zq = 0; zq < nzp; zq += 4) {
+                    SepMoments m;
+                    sep_march_xy_grad(volpad, V, dm, r, zq, m);
+                    for (int k = 0; k < 4; ++k) { S[zq + k] = m.S[k]; T[zq + k] = m.T[k]; Gx[zq + k] = m.Gx[k]; Gy[zq + k] = m.Gy[k]; TGx[zq + k] = m.TGx[k]; TGy[zq + k] = m.TGy[k]; }
+                }
+                double loc[7] = {0, 0, 0, 0, 0, 0, 0};
+                for (int iz = 0; iz < g->ndz; ++iz) {
+                    const size_t ray = (size_t)ix * g->ndz + iz;
+                    int fzp; float wz;
+                    sep_zcell(V, iz, fzp, wz);
+                    RaySums sm; sm.acc = 0.f;
+                    for (int k = 0; k < 3; ++k) { sm.s0[k] = 0.f; sm.s1[k] = 0.f; }
+                    if (fzp >= 0 && fzp <= nzp - 2) sep_ray_sums(S.data(), T.data(), Gx.data(), Gy.data(), TGx.data(), TGy.data(), fzp, wz, sm);
+                    if (proj) proj[v * n_det + ray] = sm.acc;
+                    float dp[6];
+                    ray_gradient(V, ix, iz, sm, dp);
+                    if (dproj) for (int k = 0; k < 6; ++k) dproj[((size_t)v * 6 + k) * n_det + ray] = dp[k];
+                    if (meas) {
+                        const double res = (double)meas[v * n_det + ray] - (double)sm.acc;
+                        for (int k = 0; k < 6; ++k) loc[k] += -(double)dp[k] * res;
+                        loc[6] += 0.5 * res * res;
+                    }
+                }
+#pragma omp critical
+                for (int k = 0; k < 7; ++k) red[k] += loc[k];
+            }
+            if (grad6) for (int k = 0; k < 6; ++k) grad6[v * 6 + k] = red[k];
+            if (cost) cost[v] = red[6];
+            continue;
+        }
 #pragma omp parallel for schedule(dynamic, 8)
         for (int ix = 0; ix < g->ndx; ++ix) {
             double loc[7] = {0, 0, 0, 0, 0, 0, 0};

@@ -89,9 +89,38 @@ def test_separable_forward_for_untilted_views(shape, dshape, kw):
     assert rel_l2(be.forward(vol).numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
     y = np.random.default_rng(9).random((n_proj, og.n_det)).astype(np.float32)
     assert rel_l2(be.adjoint(y).numpy(), op.adjoint(y)) <= TOL_PROJ             # separable adjoint cores
+    phi, alpha, beta, xyz = _[0], _[1], _[2], _[3]
+    out = be.proj_grad(vol, meas=y)                                              # separable gradient cores
+    for i in (1, 2, 4, 5):          # phi = 0, pi/2, pi sit exactly on lattice planes (one-sided derivative: DESIGN.md section 5)
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["proj"][i].numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][i].numpy(), gr) <= TOL_GRAD, i
+        res = y[i].astype(np.float64) - p
+        assert rel_l2(out["grad6"][i].numpy(), -gr @ res) <= TOL_GRAD
     # a tilted table is not flagged
     g2, og2, be2, op2, _ = setup(shape, dshape, 3, tilt=0.01)
     assert np.all(be2.views[:, 146] == 0.0)
+
+
+@pytest.mark.parametrize("det_pix,tilt", [((1.5, 0.75), 0.02), ((0.8, 1.5), 0.02), ((1.5, 0.75), 0.0), ((0.8, 1.5), 0.0)])
+def test_detector_pitch_differs_from_voxel_size(det_pix, tilt):
+    """Detector pixels that are not voxel sized: U and W are scaled, adjacent detector rows can share a z cell
+    (W_z = 0.75) or skip one (W_z = 1.5); tilted (generic cores) and untilted (separable cores)."""
+    shape, dshape, n_proj = (14, 16, 18), (12, 20), 5
+    g, og = make_geoms(shape, dshape, n_proj, det_pix=det_pix)
+    phi, alpha, beta, xyz = random_poses(n_proj, 13, tilt=tilt, shift=1.5)
+    be = EmuBackend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    rng = np.random.default_rng(14)
+    vol = rng.random(shape).astype(np.float32)
+    y = rng.random((n_proj, og.n_det)).astype(np.float32)
+    assert rel_l2(be.forward(vol).numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    assert rel_l2(be.adjoint(y).numpy(), op.adjoint(y)) <= TOL_PROJ
+    out = be.proj_grad(vol)
+    for i in range(n_proj):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["dproj"][i].numpy(), gr) <= TOL_GRAD
 
 
 def test_exact_lattice_pose_phi0():

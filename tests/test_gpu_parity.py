@@ -357,6 +357,18 @@ def test_separable_forward_for_untilted_views(shape, dshape, kw):
     base = torch.full(tuple(shape), 0.25, dtype=torch.float32, device="cuda")
     be.adjoint(torch.as_tensor(y), out=base, accumulate=True)
     assert rel_l2(base.cpu().numpy().ravel() - 0.25, refb) <= 2e-5
+    # separable projection + gradient (views 0, 3, 6 sit exactly on lattice planes: one-sided derivative)
+    _phi, _alpha, _beta, _xyz = _
+    outg = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(y))
+    for i in (1, 2, 4, 5):
+        p, gr = O.forward_proj_grad(og, _alpha[i], _beta[i], _phi[i], _xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(outg["proj"][i].cpu().numpy(), p) <= TOL_PROJ
+        assert rel_l2(outg["dproj"][i].cpu().numpy(), gr) <= TOL_GRAD, i
+        res = y[i].astype(np.float64) - p
+        assert rel_l2(outg["grad6"][i].cpu().numpy(), -gr @ res) <= TOL_GRAD
+        assert abs(outg["cost"][i].item() - 0.5 * res @ res) <= 1e-5 * (0.5 * res @ res)
+    out2 = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(y))
+    assert torch.equal(out2["grad6"], outg["grad6"]) and torch.equal(out2["dproj"], outg["dproj"])
     # mixed table: views 1, 4 tilted
     phi, alpha, beta, xyz = random_poses(n_proj, 3, tilt=0.0, phis=phis)
     alpha[[1, 4]] = [0.01, -0.02]
@@ -365,6 +377,37 @@ def test_separable_forward_for_untilted_views(shape, dshape, kw):
     mixed = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
     assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), mixed.forward(vol)) <= TOL_PROJ
     assert rel_l2(be.adjoint(torch.as_tensor(y)).cpu().numpy(), mixed.adjoint(y)) <= TOL_PROJ
+    outm = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(y))
+    for i in (1, 2, 4, 5):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(outm["dproj"][i].cpu().numpy(), gr) <= TOL_GRAD, i
+        assert rel_l2(outm["grad6"][i].cpu().numpy(), -gr @ (y[i].astype(np.float64) - p)) <= TOL_GRAD, i
+
+
+@pytest.mark.parametrize("det_pix,tilt", [((1.5, 0.75), 0.02), ((0.8, 1.5), 0.02), ((1.5, 0.75), 0.0), ((0.8, 1.5), 0.0),
+                                          ((1.0, 0.62), 0.03)])
+def test_detector_pitch_differs_from_voxel_size(det_pix, tilt):
+    """W_z = 0.75 / 0.62: adjacent lanes of the tile kernel share z cells all the time (second-pass deferral);
+    W_z = 1.5: rows skip cells; untilted variants run the separable kernels (3-tap z gather)."""
+    shape, dshape, n_proj = (44, 40, 70), (40, 90), 6
+    g, og = make_geoms(shape, dshape, n_proj, det_pix=det_pix)
+    phi, alpha, beta, xyz = random_poses(n_proj, 13, tilt=tilt, shift=1.5)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    rng = np.random.default_rng(14)
+    vol = rng.random(shape).astype(np.float32)
+    y = rng.random((n_proj, og.n_det)).astype(np.float32)
+    assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    refb = op.adjoint(y)
+    got = be.adjoint(torch.as_tensor(y))
+    assert rel_l2(got.cpu().numpy(), refb) <= TOL_PROJ
+    assert rel_l2(be.adjoint(torch.as_tensor(y), gather=True).cpu().numpy(), refb) <= TOL_PROJ
+    assert torch.equal(be.adjoint(torch.as_tensor(y)), got)
+    out = be.proj_grad(torch.as_tensor(vol))
+    for i in range(n_proj):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["dproj"][i].cpu().numpy(), gr) <= TOL_GRAD
 
 
 def test_error_codes_surface_as_exceptions():

@@ -40,7 +40,7 @@ struct RayArgs {
     int nx, ny, nz, ndx, ndz, n_proj;
     int sxp, syp;            // padded strides (floats) of x and y; z stride is 1
     int nxt, nzt;            // detector tiles along x and z
-    int skip_separable;      // forward only: leave views with V_SEP == 1 to sep_forward_kernel
+    int skip_separable;      // leave views with V_SEP == 1 to the separable kernels
 };
 
 template <bool GRAD>
@@ -55,7 +55,7 @@ __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
     const bool active = (ix < A.ndx) && (iz < A.ndz);
 
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
-    if (!GRAD && A.skip_separable && V[V_SEP] != 0.0) return;      // untilted view: sep_forward_kernel does it
+    if (A.skip_separable && V[V_SEP] != 0.0) return;               // untilted view (block-uniform): the separable kernels do it
     const size_t n_det = (size_t)A.ndx * A.ndz;
     const size_t ray = (size_t)ix * A.ndz + iz;
 
@@ -111,12 +111,14 @@ __global__ void __launch_bounds__(TILE_Z * TILE_X) ray_kernel_gradient(const Ray
 
 // Second pass of the deterministic reduction: one thread per (view, component) sums the block
 // partials of that view in (zt, xt) order.
-__global__ void grad_finalize_kernel(const double* __restrict__ partial, int n_proj, int nxt, int nzt,
-                                     double* __restrict__ grad6, double* __restrict__ cost)
+__global__ void grad_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ views, int want_sep,
+                                     int n_proj, int nxt, int nzt, double* __restrict__ grad6, double* __restrict__ cost)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_proj * NRED) return;
     const int view = t / NRED, k = t % NRED;
+    // tilted views were reduced by ray_kernel_gradient, untilted ones by sep_gradient_kernel (own tiling)
+    if ((views[(size_t)view * TOMO_VIEW_STRIDE + V_SEP] != 0.0) != (want_sep != 0)) return;
     double v = 0.0;
     for (int zt = 0; zt < nzt; ++zt)
         for (int xt = 0; xt < nxt; ++xt)
@@ -147,6 +149,9 @@ extern "C" void tomo_set_error(const char* msg);
 int tomo_check_cuda(cudaError_t e, const char* what);
 int tomo_forward_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* volpad, float* proj,
                                   void* stream);
+void tomo_grad_separable_tiles(const TomoGeom* g, int* nxt, int* nchunk);
+int tomo_grad_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* volpad, const float* meas,
+                               float* proj, float* dproj, double* partial, void* stream);
 
 static int check_sizes(const TomoGeom* g)
 {
@@ -208,7 +213,10 @@ extern "C" size_t tomo_proj_grad_workspace_bytes(const TomoGeom* g, int n_proj)
 {
     if (!g || n_proj <= 0) return 0;
     const size_t nxt = (g->ndx + TILE_X - 1) / TILE_X, nzt = (g->ndz + TILE_Z - 1) / TILE_Z;
-    return sizeof(double) * NRED * nxt * nzt * (size_t)n_proj;
+    int sxt, sch;
+    tomo_grad_separable_tiles(g, &sxt, &sch);
+    // block partials of ray_kernel_gradient followed by those of sep_gradient_kernel
+    return sizeof(double) * NRED * (nxt * nzt + (size_t)sxt * sch) * (size_t)n_proj;
 }
 
 extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
@@ -228,12 +236,19 @@ extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
         }
         A.partial = (double*)workspace;
     }
+    A.skip_separable = 1;
     const dim3 block(TILE_Z, TILE_X);
     ray_kernel_gradient<<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
     if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_gradient")) return e;
+    // untilted views: separable kernel with its own block partials behind the generic ones
+    double* sep_partial = reduce ? A.partial + (size_t)NRED * A.nxt * A.nzt * n_proj : nullptr;
+    if (int e = tomo_grad_separable_launch(g, views, n_proj, volpad, meas, proj, dproj, sep_partial, stream)) return e;
     if (reduce) {
         const int n = n_proj * NRED;
-        grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, n_proj, A.nxt, A.nzt, grad6, cost);
+        int sxt, sch;
+        tomo_grad_separable_tiles(g, &sxt, &sch);
+        grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, A.views, 0, n_proj, A.nxt, A.nzt, grad6, cost);
+        grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sep_partial, A.views, 1, n_proj, sxt, sch, grad6, cost);
         return tomo_check_cuda(cudaGetLastError(), "grad_finalize_kernel");
     }
     return 0;

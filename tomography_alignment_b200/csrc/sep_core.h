@@ -173,3 +173,81 @@ TOMO_HD float sep_column_weight(const double* __restrict__ V, const SepColumn& c
     }
     return K;
 }
+
+// ---- separable projection + gradient (untilted views) --------------------------------------------------------
+// Per (ix, z plane) the march accumulates six moments of the in-plane bilinear interpolant B and its one-sided
+// in-plane derivatives (same cells as src/ray_wt_grad.f90:142-220: the (x, y) fraction is carried as 64-bit fixed
+// point so every cell is the float64 one):
+//     S = sum B,  T = sum j B,  Gx = sum dB/dx,  Gy = sum dB/dy,  TGx = sum j dB/dx,  TGy = sum j dB/dy
+// and a ray (ix, iz) with z cell fz and weight wz gets
+//     proj = lerp(S),  S0 = (lerp(Gx), lerp(Gy), S[fz+1] - S[fz]),  S1 = (lerp(TGx), lerp(TGy), T[fz+1] - T[fz]).
+struct SepMoments { float S[4], T[4], Gx[4], Gy[4], TGx[4], TGy[4]; };
+
+TOMO_HD f2 f2_add(f2 a, f2 b) { return f2_fma(a, f2_make(1.f, 1.f), b); }
+
+TOMO_HD void sep_march_xy_grad(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                               const SepSetup& r, int zq, SepMoments& m)
+{
+    const int ust[2] = {dm.sxp, dm.syp};
+    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1];
+    unsigned fh[2], fl[2], dh[2], dl[2];
+    int off = zq;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const double q = (double)r.sg[a] * (r.p[a] + (double)r.j0 * r.D[a]);
+        const double qi = floor(q);
+        const unsigned long long f64 = (unsigned long long)((q - qi) * 18446744073709551616.0);
+        const double ad = fabs(r.D[a]);
+        const unsigned long long d64 = (unsigned long long)((ad - floor(ad)) * 18446744073709551616.0);
+        fh[a] = (unsigned)(f64 >> 32); fl[a] = (unsigned)f64;
+        dh[a] = (unsigned)(d64 >> 32); dl[a] = (unsigned)d64;
+        off += (TOMO_PAD + r.sg[a] * (int)qi) * ust[a];
+    }
+    f2 S0 = f2_make(0.f, 0.f), S1 = S0, T0 = S0, T1 = S0, X0 = S0, X1 = S0, Y0 = S0, Y1 = S0, TX0 = S0, TX1 = S0, TY0 = S0, TY1 = S0;
+    float fj = (float)r.j0;
+    for (int j = r.j0; j < r.j1; ++j) {
+        const float fx = fix_to_float(fh[0]), fy = fix_to_float(fh[1]);
+        const float* __restrict__ c = vol + off;
+        const f4 v00 = sep_ld4(c), v01 = sep_ld4(c + o01), v10 = sep_ld4(c + o10), v11 = sep_ld4(c + o11);
+        const f2 fy2 = f2_make(fy, fy), fx2 = f2_make(fx, fx), fj2 = f2_make(fj, fj);
+        // planes 0,1 (.x, .y) and planes 2,3 (.z, .w) as two register pairs
+#define SEP_GRAD_HALF(a00, a01, a10, a11, Sq, Tq, Xq, Yq, TXq, TYq)                                   \
+        {                                                                                             \
+            const f2 dy0 = f2_sub(a01, a00), dy1 = f2_sub(a11, a10);                                  \
+            const f2 y0 = f2_fma(fy2, dy0, a00), y1 = f2_fma(fy2, dy1, a10);                          \
+            const f2 gx = f2_sub(y1, y0);                                                             \
+            const f2 val = f2_fma(fx2, gx, y0);                                                       \
+            const f2 gy = f2_fma(fx2, f2_sub(dy1, dy0), dy0);                                         \
+            Sq = f2_add(val, Sq);  Tq = f2_fma(fj2, val, Tq);                                         \
+            Xq = f2_add(gx, Xq);   TXq = f2_fma(fj2, gx, TXq);                                        \
+            Yq = f2_add(gy, Yq);   TYq = f2_fma(fj2, gy, TYq);                                        \
+        }
+        SEP_GRAD_HALF(f2_make(v00.x, v00.y), f2_make(v01.x, v01.y), f2_make(v10.x, v10.y), f2_make(v11.x, v11.y), S0, T0, X0, Y0, TX0, TY0)
+        SEP_GRAD_HALF(f2_make(v00.z, v00.w), f2_make(v01.z, v01.w), f2_make(v10.z, v10.w), f2_make(v11.z, v11.w), S1, T1, X1, Y1, TX1, TY1)
+#undef SEP_GRAD_HALF
+        fj += 1.0f;
+        off += r.stepoff;
+        off += (int)fix64_add(fh[0], fl[0], dh[0], dl[0]) * r.st[0];
+        off += (int)fix64_add(fh[1], fl[1], dh[1], dl[1]) * r.st[1];
+    }
+    const float sx = (float)r.sg[0], sy = (float)r.sg[1];      // derivatives w.r.t. the real (un-mirrored) coordinates
+    m.S[0] = S0.x; m.S[1] = S0.y; m.S[2] = S1.x; m.S[3] = S1.y;
+    m.T[0] = T0.x; m.T[1] = T0.y; m.T[2] = T1.x; m.T[3] = T1.y;
+    m.Gx[0] = sx * X0.x; m.Gx[1] = sx * X0.y; m.Gx[2] = sx * X1.x; m.Gx[3] = sx * X1.y;
+    m.Gy[0] = sy * Y0.x; m.Gy[1] = sy * Y0.y; m.Gy[2] = sy * Y1.x; m.Gy[3] = sy * Y1.y;
+    m.TGx[0] = sx * TX0.x; m.TGx[1] = sx * TX0.y; m.TGx[2] = sx * TX1.x; m.TGx[3] = sx * TX1.y;
+    m.TGy[0] = sy * TY0.x; m.TGy[1] = sy * TY0.y; m.TGy[2] = sy * TY1.x; m.TGy[3] = sy * TY1.y;
+}
+
+// Ray sums from the six plane arrays (each indexed by plane; k = floor plane index into them)
+TOMO_HD void sep_ray_sums(const float* S, const float* T, const float* Gx, const float* Gy, const float* TGx,
+                          const float* TGy, int k, float wz, RaySums& out)
+{
+    out.acc = fmaf(wz, S[k + 1] - S[k], S[k]);
+    out.s0[0] = fmaf(wz, Gx[k + 1] - Gx[k], Gx[k]);
+    out.s0[1] = fmaf(wz, Gy[k + 1] - Gy[k], Gy[k]);
+    out.s0[2] = S[k + 1] - S[k];
+    out.s1[0] = fmaf(wz, TGx[k + 1] - TGx[k], TGx[k]);
+    out.s1[1] = fmaf(wz, TGy[k + 1] - TGy[k], TGy[k]);
+    out.s1[2] = T[k + 1] - T[k];
+}

@@ -71,6 +71,105 @@ sep_forward_kernel(const SepArgs A)
     }
 }
 
+// ---- separable projection + gradient -----------------------------------------------------------------------------
+struct SepGradArgs {
+    const float*  volpad;
+    const double* views;
+    const float*  meas;      // nullable
+    float*        proj;      // nullable
+    float*        dproj;     // nullable
+    double*       partial;   // nullable, [nchunk][n_proj][nxt][7]
+    int nx, ny, nz, ndx, ndz, n_proj, sxp, syp, nzp;
+    int nxt, nchunk;
+};
+
+#ifndef SEP_GRAD_MINB
+#define SEP_GRAD_MINB 4      // 64 registers (4 blocks/SM) measured best: 26.5 ms vs 45 ms at ptxas' own 102
+#endif
+__global__ void __launch_bounds__(32 * SEP_WARPS, SEP_GRAD_MINB)
+sep_gradient_kernel(const SepGradArgs A)
+{
+    __shared__ float M[SEP_WARPS][6][SEP_CHUNK];
+    __shared__ double red_sm[SEP_WARPS][7];
+    const long long item = blockIdx.x;
+    const int xt = (int)(item % A.nxt);
+    const int view = (int)((item / A.nxt) % A.n_proj);
+    const int chunk = (int)(item / ((long long)A.nxt * A.n_proj));
+    const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+    if (V[V_SEP] == 0.0) return;                                   // tilted view (block-uniform): ray_kernel_gradient does it
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int ix = xt * SEP_WARPS + warp;
+    const bool row = ix < A.ndx;                                   // warp-uniform
+    const RayDims dm = {A.nx, A.ny, A.nz, A.sxp, A.syp};
+    const int zp0 = chunk * SEP_OUT;
+    const int zq = zp0 + 4 * lane;
+    SepMoments m;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m.S[k] = m.T[k] = m.Gx[k] = m.Gy[k] = m.TGx[k] = m.TGy[k] = 0.f; }
+    if (row && zq < A.nzp) {
+        SepSetup r;
+        sep_setup(V, dm, ix, r);
+        sep_march_xy_grad(A.volpad, V, dm, r, zq, m);
+    }
+    *reinterpret_cast<float4*>(&M[warp][0][4 * lane]) = make_float4(m.S[0], m.S[1], m.S[2], m.S[3]);
+    *reinterpret_cast<float4*>(&M[warp][1][4 * lane]) = make_float4(m.T[0], m.T[1], m.T[2], m.T[3]);
+    *reinterpret_cast<float4*>(&M[warp][2][4 * lane]) = make_float4(m.Gx[0], m.Gx[1], m.Gx[2], m.Gx[3]);
+    *reinterpret_cast<float4*>(&M[warp][3][4 * lane]) = make_float4(m.Gy[0], m.Gy[1], m.Gy[2], m.Gy[3]);
+    *reinterpret_cast<float4*>(&M[warp][4][4 * lane]) = make_float4(m.TGx[0], m.TGx[1], m.TGx[2], m.TGx[3]);
+    *reinterpret_cast<float4*>(&M[warp][5][4 * lane]) = make_float4(m.TGy[0], m.TGy[1], m.TGy[2], m.TGy[3]);
+    __syncwarp();
+    double red[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (row) {
+        const double z0 = V[V_P00 + 2], wzv = V[V_W + 2];
+        const int last = (chunk == A.nchunk - 1);
+        const int iz_lo = (chunk == 0) ? 0 : (int)fmin(fmax(ceil(((double)(zp0 - TOMO_PAD) - z0) / wzv) - 1.0, 0.0), (double)A.ndz);
+        const int iz_hi = last ? A.ndz : (int)fmin(fmax(ceil(((double)(zp0 + SEP_OUT - TOMO_PAD) - z0) / wzv) + 1.0, 0.0), (double)A.ndz);
+        const size_t n_det = (size_t)A.ndx * A.ndz;
+        for (int iz = iz_lo + lane; iz < iz_hi; iz += 32) {
+            int fzp; float wz;
+            sep_zcell(V, iz, fzp, wz);
+            const int fc = min(max(fzp, 0), A.nzp - 2);
+            if (min(fc / SEP_OUT, A.nchunk - 1) != chunk) continue;
+            RaySums sm;
+            sm.acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sm.s0[k] = 0.f; sm.s1[k] = 0.f; }
+            if (fzp >= 0 && fzp <= A.nzp - 2)
+                sep_ray_sums(M[warp][0], M[warp][1], M[warp][2], M[warp][3], M[warp][4], M[warp][5], fzp - zp0, wz, sm);
+            const size_t ray = (size_t)ix * A.ndz + iz;
+            if (A.proj) A.proj[(size_t)view * n_det + ray] = sm.acc;
+            float dp[6];
+            ray_gradient(V, ix, iz, sm, dp);
+            if (A.dproj) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) A.dproj[((size_t)view * 6 + k) * n_det + ray] = dp[k];
+            }
+            if (A.meas) {
+                const double res = (double)A.meas[(size_t)view * n_det + ray] - (double)sm.acc;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) red[k] += -(double)dp[k] * res;
+                red[6] += 0.5 * res * res;
+            }
+        }
+    }
+    if (A.partial) {        // fixed-order block reduction, as in ray_kernel_gradient
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            double v = red[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) red_sm[warp][k] = v;
+        }
+        __syncthreads();
+        if (warp == 0 && lane < 7) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < SEP_WARPS; ++w) v += red_sm[w][lane];
+            A.partial[(size_t)blockIdx.x * 7 + lane] = v;
+        }
+    }
+}
+
 // ---- separable adjoint ------------------------------------------------------------------------------------------
 constexpr int SA_WARPS_X = 4, SA_WARPS_Y = 4;        // a block = 4 x 4 voxel columns, one warp each
 constexpr int SA_QPL = 4;                            // z quads per lane: a warp covers 32 * 4 * 4 = 512 planes
@@ -197,4 +296,30 @@ int tomo_back_separable_launch(const TomoGeom* g, const void* views, int n_proj,
     if (grid.y > 65535u || grid.z > 65535u) { tomo_set_error("separable adjoint: volume too large for the launch grid"); return TOMO_E_RANGE; }
     sep_adjoint_kernel<<<grid, dim3(32, SA_WARPS_Y, SA_WARPS_X), 0, (cudaStream_t)stream>>>(A);
     return tomo_check_cuda(cudaGetLastError(), "sep_adjoint_kernel");
+}
+
+// Tiling of the separable gradient (for the workspace layout and the finalize pass)
+void tomo_grad_separable_tiles(const TomoGeom* g, int* nxt, int* nchunk)
+{
+    const int nzp = tomo_nzp(g->nz);
+    *nxt = (g->ndx + SEP_WARPS - 1) / SEP_WARPS;
+    int nc = (nzp - 1 + SEP_OUT - 1) / SEP_OUT;
+    while ((nc - 1) * SEP_OUT + SEP_CHUNK < nzp) ++nc;
+    *nchunk = nc;
+}
+
+int tomo_grad_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* volpad, const float* meas,
+                               float* proj, float* dproj, double* partial, void* stream)
+{
+    SepGradArgs A;
+    A.volpad = volpad; A.views = (const double*)views; A.meas = meas; A.proj = proj; A.dproj = dproj; A.partial = partial;
+    A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
+    A.nzp = tomo_nzp(g->nz);
+    A.syp = A.nzp;
+    A.sxp = (g->ny + 2 * TOMO_PAD) * A.syp;
+    tomo_grad_separable_tiles(g, &A.nxt, &A.nchunk);
+    const double nblocks = (double)A.nxt * A.nchunk * n_proj;
+    if (nblocks >= 2147483647.0) { tomo_set_error("separable gradient: too many blocks for one launch"); return TOMO_E_RANGE; }
+    sep_gradient_kernel<<<(unsigned)nblocks, dim3(32, SEP_WARPS), 0, (cudaStream_t)stream>>>(A);
+    return tomo_check_cuda(cudaGetLastError(), "sep_gradient_kernel");
 }

@@ -327,5 +327,5 @@ class CudaBackend(object):
                                          _ptr(grad6), _ptr(cost), _ptr(self._ws) if want_grad6 else None,
                                          ws_bytes, self._stream())
         _lib.check(rc, "tomo_proj_grad")
-        self.launches += 2 if want_grad6 else 1
+        self.launches += 4 if want_grad6 else 2   # ray + separable gradient kernels (+ two finalize passes)
         return {"proj": proj, "dproj": dproj, "grad6": grad6, "cost": cost}
