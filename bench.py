@@ -38,6 +38,16 @@ UNIT = "voxel-ray updates/s"
 
 _T0 = time.perf_counter()
 
+# stdout carries exactly one JSON line: keep a private handle on the real stdout and point fd 1 at stderr, so that
+# nothing a library prints there (NCCL's version banner, for one) can end up next to the result
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 def log(msg):
     """Progress to stderr (stdout carries only the JSON line)."""
@@ -108,7 +118,7 @@ def run_reference(a):
             "cpu_baseline": info,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -168,8 +178,6 @@ class ClockSampler(object):
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
 def run_b200(a):
-    # keep stdout to the one JSON line: NCCL prints its version banner (and warnings) to stdout by default
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from tomography_alignment_b200 import Geometry, ProjectionMatrix, pose_table
@@ -346,20 +354,42 @@ def run_b200(a):
         h_bp = torch.empty((n, n, n), dtype=torch.float32).pin_memory()
         log("pinned host buffers ready")
 
-        h_g6 = None
+        d_vol = torch.empty((n, n, n), dtype=torch.float32, device=dev)
+        g_tab = torch.zeros((n_proj, 7), dtype=torch.float64, device=dev)
+
+        def upload_volume():
+            """The replicated volume: rank 0 uploads it from pinned host memory, the other ranks receive it over NVLink
+            (what the bcast of recon/regularized_mpi.py:137 does, on the device)."""
+            if world == 1:
+                return None
+            if rank == 0:
+                d_vol.copy_(h_vol, non_blocking=True)
+                be.h2d_bytes += 4 * h_vol.numel()
+            dist.broadcast(d_vol, src=0)
+            return d_vol
 
         def e2e_step():
             # host buffers in, host buffers out; copies are issued inside the calls (view chunks, side stream)
-            A._backend.forward_host(h_vol, out_host=h_proj)          # H2D volume, forward, D2H projections
+            be.forward_host(h_vol, out_host=h_proj, vol_dev=upload_volume())   # H2D volume, forward, D2H projections
             if world == 1:
-                A._backend.adjoint_host(h_meas, out_host=h_bp)       # H2D projections, adjoint, D2H volume
-            else:                                                    # Allreduce of recon/sirt_mpi.py:103 before the D2H
-                v = A._backend.adjoint_host(h_meas, out_host=None, to_host=False)
+                be.adjoint_host(h_meas, out_host=h_bp)                          # H2D projections, adjoint, D2H volume
+            else:                                                               # Allreduce of recon/sirt_mpi.py:103, then rank 0 downloads
+                v = be.adjoint_host(h_meas, out_host=None, to_host=False)
                 dist.all_reduce(v)
-                h_bp.copy_(v)
-                A._backend.d2h_bytes += 4 * v.numel()
-            g6, c = A._backend.proj_grad_host(h_vol, h_meas)         # H2D volume + measured, D2H (n, 6) gradients
-            return g6, c
+                if rank == 0:
+                    h_bp.copy_(v)
+                    be.d2h_bytes += 4 * v.numel()
+            if world == 1:
+                return be.proj_grad_host(h_vol, h_meas)                         # H2D volume + measured, D2H (n, 6) gradients
+            g6, c = be.proj_grad_host(None, h_meas, vol_dev=upload_volume(), to_host=False)
+            g_tab.zero_()
+            g_tab[idx, :6] = g6
+            g_tab[idx, 6] = c
+            dist.all_reduce(g_tab)                                              # zero-padded all-reduce = all-gather
+            out = g_tab.cpu() if rank == 0 else None
+            if rank == 0:
+                be.d2h_bytes += 8 * g_tab.numel()
+            return out
 
         e2e_step()
         sync_all()
@@ -395,7 +425,7 @@ def run_b200(a):
                            "phantom": "shepp3d", "poses": "examples/generate_data.py jitter, seed 20240229"},
                 "roofline": roofline, "untilted_poses": untilted, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "impl": "b200"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -161,19 +161,25 @@ class CudaBackend(object):
         return out
 
     # -- host-buffer entry points: copies overlapped with the kernels in view chunks ------------------
-    def forward_host(self, x_host, out_host=None, chunk_views=None):
+    def forward_host(self, x_host, out_host=None, chunk_views=None, vol_dev=None):
         """proj = A x with HOST input and output (numpy or CPU tensors; pinned memory makes the copies
         asynchronous).  The volume goes up once; the views are projected in chunks and each chunk's
-        device->host copy runs on a side stream under the next chunk's kernel."""
-        x_host = self._host(x_host).reshape(-1)
-        if x_host.numel() != int(np.prod(self.vol_shape)):
-            raise ValueError("volume has %d elements, geometry expects %d" % (x_host.numel(), int(np.prod(self.vol_shape))))
+        device->host copy runs on a side stream under the next chunk's kernel.
+        ``vol_dev``: the volume is already on this device (e.g. broadcast from the rank that uploaded it)."""
+        if vol_dev is None:
+            x_host = self._host(x_host).reshape(-1)
+            if x_host.numel() != int(np.prod(self.vol_shape)):
+                raise ValueError("volume has %d elements, geometry expects %d" % (x_host.numel(), int(np.prod(self.vol_shape))))
         if out_host is None:
             out_host = torch.empty((self.n_proj,) + self.det_shape, dtype=torch.float32, pin_memory=True)
         out3 = out_host.reshape((self.n_proj,) + self.det_shape)
         cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
-        vol_d = self._buf("vol", self.vol_shape)
-        vol_d.reshape(-1).copy_(x_host, non_blocking=True)
+        if vol_dev is None:
+            vol_d = self._buf("vol", self.vol_shape)
+            vol_d.reshape(-1).copy_(x_host, non_blocking=True)
+            self.h2d_bytes += 4 * x_host.numel()
+        else:
+            vol_d = self._as_vol(vol_dev)
         volpad = self.pad(vol_d)
         proj_d = self._buf("proj", (self.n_proj,) + self.det_shape)
         with torch.cuda.device(self.device):
@@ -188,7 +194,6 @@ class CudaBackend(object):
                     out3[a:b].copy_(proj_d[a:b], non_blocking=True)
         cp.synchronize()
         cur.wait_stream(cp)
-        self.h2d_bytes += 4 * x_host.numel()
         self.d2h_bytes += 4 * out3.numel()
         return out_host
 
@@ -230,12 +235,14 @@ class CudaBackend(object):
         self.d2h_bytes += 4 * out_host.numel()
         return out_host
 
-    def proj_grad_host(self, vol_host, meas_host, chunk_views=None):
+    def proj_grad_host(self, vol_host, meas_host, chunk_views=None, vol_dev=None, to_host=True):
         """Fused residual gradients with HOST inputs: returns (grad6 (n_proj, 6), cost (n_proj,)) float64 CPU
-        tensors.  The measured projections go up in chunks under the previous chunk's kernel."""
-        vol_host = self._host(vol_host).reshape(-1)
+        tensors (device tensors with ``to_host=False``).  The measured projections go up in chunks under the
+        previous chunk's kernel.  ``vol_dev``: the volume is already on this device."""
         meas_host = self._host(meas_host)
-        if vol_host.numel() != int(np.prod(self.vol_shape)) or meas_host.numel() != self.n_proj * self.n_det:
+        if vol_dev is None:
+            vol_host = self._host(vol_host).reshape(-1)
+        if (vol_dev is None and vol_host.numel() != int(np.prod(self.vol_shape))) or meas_host.numel() != self.n_proj * self.n_det:
             raise ValueError("volume / measured projections do not match the geometry and the current poses")
         meas_host = meas_host.reshape(self.n_proj, -1)
         cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
@@ -252,7 +259,11 @@ class CudaBackend(object):
                 ev = torch.cuda.Event()
                 ev.record(cp)
                 evs.append(ev)
-        vol_d.reshape(-1).copy_(vol_host, non_blocking=True)
+        if vol_dev is None:
+            vol_d.reshape(-1).copy_(vol_host, non_blocking=True)
+            self.h2d_bytes += 4 * vol_host.numel()
+        else:
+            vol_d = self._as_vol(vol_dev)
         volpad = self.pad(vol_d)
         cmax = max(b - a for a, b in chunks)
         ws_bytes = self.lib.tomo_proj_grad_workspace_bytes(self._g(), cmax)
@@ -265,8 +276,10 @@ class CudaBackend(object):
                                              _ptr(grad6[a:b]), _ptr(cost[a:b]), _ptr(self._ws), ws_bytes, self._stream())
                 _lib.check(rc, "tomo_proj_grad")
                 self.launches += 2
+        self.h2d_bytes += 4 * meas_host.numel()
+        if not to_host:
+            return grad6, cost
         g6, c = grad6.cpu(), cost.cpu()          # synchronises `cur`
-        self.h2d_bytes += 4 * (vol_host.numel() + meas_host.numel())
         self.d2h_bytes += 8 * (g6.numel() + c.numel())
         return g6, c
 
