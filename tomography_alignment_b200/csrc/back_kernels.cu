@@ -23,6 +23,9 @@
 //         lanes, W_z < 1); those lanes are deferred to a second pass;
 //       * the four z-floor corners and the four z-ceil corners are separated by __syncwarp (lane l's
 //         ceil plane is lane l+1's floor plane).
+//     The inner loop is branch-free: a lane outside its sample range is redirected to dummy cells in its
+//     own bank (guard / ghost area) instead of being predicated off, and the corner pairs go through
+//     packed fp32x2 FMAs -- 52 SASS instructions per warp-sample (16 of them the LDS/STS of the 8 RMWs).
 //     A sample is handled by every tile that owns one of its corner voxels; contributions that land
 //     on the tile's ghost cells are dropped (the neighbouring tile adds them), so each voxel sums
 //     exactly the reference's terms, in a fixed order: results are bitwise reproducible.
@@ -111,31 +114,16 @@ struct TileView {
     float dupthr;           // same-z-cell test threshold for adjacent lanes
 };
 
-// Four read-modify-writes acc[off_k] += w_k * wz on shared memory, predicated on `act`, as one PTX block:
-// no branch, no reconvergence barrier; the four loads are issued before the first store.
+// Four read-modify-writes s[off_k] += w_k * wz on shared memory as two packed fp32x2 FMAs; the four loads
+// are issued before the first store.  There is no predicate: a lane with nothing to add is pointed at its
+// own dummy cells (see tile_march_view), one select instead of a divergent branch + reconvergence barrier.
 template <int O1, int O2, int O3>
-__device__ __forceinline__ void rmw4(float* s, bool act, float w0, float w1, float w2, float w3, float wz)
+__device__ __forceinline__ void rmw4(float* s, float2 wA, float2 wB, float wz)
 {
-#if defined(TOMO_TILE_PTX_RMW)
-    const unsigned a = (unsigned)__cvta_generic_to_shared(s);
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .f32 a0, a1, a2, a3;\n\t"
-        "setp.ne.u32 p, %0, 0;\n\t"
-        "@p ld.shared.f32 a0, [%1];\n\t@p ld.shared.f32 a1, [%1+%7];\n\t"
-        "@p ld.shared.f32 a2, [%1+%8];\n\t@p ld.shared.f32 a3, [%1+%9];\n\t"
-        "fma.rn.f32 a0, %2, %6, a0;\n\tfma.rn.f32 a1, %3, %6, a1;\n\t"
-        "fma.rn.f32 a2, %4, %6, a2;\n\tfma.rn.f32 a3, %5, %6, a3;\n\t"
-        "@p st.shared.f32 [%1], a0;\n\t@p st.shared.f32 [%1+%7], a1;\n\t"
-        "@p st.shared.f32 [%1+%8], a2;\n\t@p st.shared.f32 [%1+%9], a3;\n\t}"
-        :: "r"((unsigned)act), "r"(a), "f"(w0), "f"(w1), "f"(w2), "f"(w3), "f"(wz),
-           "n"(O1 * 4), "n"(O2 * 4), "n"(O3 * 4) : "memory");
-#else
-    if (act) {
-        const float a0 = s[0], a1 = s[O1], a2 = s[O2], a3 = s[O3];
-        s[0] = fmaf(w0, wz, a0); s[O1] = fmaf(w1, wz, a1);
-        s[O2] = fmaf(w2, wz, a2); s[O3] = fmaf(w3, wz, a3);
-    }
-#endif
+    const float2 aA = make_float2(s[0], s[O1]), aB = make_float2(s[O2], s[O3]);
+    const float2 z2 = make_float2(wz, wz);
+    const float2 rA = __ffma2_rn(wA, z2, aA), rB = __ffma2_rn(wB, z2, aB);
+    s[0] = rA.x; s[O1] = rA.y; s[O2] = rB.x; s[O3] = rB.y;
 }
 
 // March the rays of one view through the tile.  SGX/SGY/SGZ = sign of D per axis: with the mirrored
@@ -148,7 +136,17 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
     constexpr int STX = SGX * TSY * TSZ, STY = SGY * TSZ, STZ = SGZ;
     constexpr int O01 = STY, O10 = STX, O11 = STX + STY, OZ = STZ;
     const float hi[3] = {(float)(TOMO_BT_X + 1), (float)(TOMO_BT_Y + 1), (float)(TOMO_BT_Z + 1)};
-    const int stepoff = tv.di_step;
+    const int stepoff = tv.di_step, stepx = tv.di_step + STX;
+    // Dummy cells: a lane with nothing to add is redirected to (its own bank) + DUMMY, so it stays conflict-free
+    // against the active lanes.  The eight corner offsets span [OMIN, OMIN + TGUARD - 1]; with DUMMY = -OMIN
+    // rounded up to a multiple of 32 every dummy access falls into the front guard or the x = 0 ghost plane of the
+    // tile (never read back).  smem_raw is 128-byte aligned, so "own bank" is bits 2..6 of the shared address.
+    constexpr int OMIN = (STX < 0 ? STX : 0) + (STY < 0 ? STY : 0) + (STZ < 0 ? STZ : 0);
+    constexpr int DUMMY = ((-OMIN + 31) / 32) * 32;
+    static_assert(DUMMY + 31 + OMIN + TGUARD - 1 < TGUARD + TSY * TSZ, "dummy cells leave the ghost plane");
+    const unsigned acc_b = (unsigned)__cvta_generic_to_shared(acc);
+    unsigned dummy_b = acc_b - 4u * TGUARD + 4u * DUMMY;
+    asm volatile("" : "+r"(dummy_b));                       // a register, not a per-sample recomputation
     for (int c = 0; c < tv.ncol; ++c) {
         const int first = tv.ix_lo + (((c - tv.ix_lo) % tv.ncol) + tv.ncol) % tv.ncol;
         for (int ix = first + tv.ncol * warp; ix <= tv.ix_hi; ix += tv.ncol * TNW) {
@@ -176,8 +174,9 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                 if (jw0 >= jw1) continue;                                   // warp-uniform
                 const bool live = j1 > j0;
                 const float yv = live ? __ldg(P + (size_t)ix * ndz + iz) : 0.f;
-                const unsigned span = live ? (unsigned)(j1 - j0) : 0u;
+                unsigned span = live ? (unsigned)(j1 - j0) : 0u;
                 unsigned k = (unsigned)(jw0 - (live ? j0 : 0));             // j - j0, wraps below zero
+                asm volatile("" : "+r"(span));                              // keep it in a register (no per-sample recompute)
 
                 // mirrored-frame state at sample jw0
                 const float fj = (float)jw0;
@@ -187,39 +186,46 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                 const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
                 float f0 = qx - flx, f1 = qy - fly, f2 = qz - flz;
                 int off = (int)flx * STX + (int)fly * STY + (int)flz * STZ;
-                float* __restrict__ s = acc + off;
+                unsigned sb = acc_b + 4u * (unsigned)off;                  // shared byte address of the floor cell
+                const float2 yv2 = make_float2(yv, yv);
                 for (int j = jw0; j < jw1; ++j) {
                     const bool act = k < span;
                     // lane l+1 sits in lane l's z cell iff its own fraction says so (no shuffle needed):
                     // mirrored z decreases (SGZ < 0) or increases (SGZ > 0) by W_z per lane
                     const bool dup = act && ((SGZ > 0) ? (f2 >= tv.dupthr) : (f2 < 1.f - tv.dupthr));
+                    // corner weights as the pairs (x0y0, x1y0) and (x0y1, x1y1) of the packed FMAs
                     const float wx1 = f0 * yv, wx0 = yv - wx1;
-                    const float wy0 = 1.f - f1, wz0 = 1.f - f2;
-                    const float w00 = wx0 * wy0, w01 = wx0 * f1, w10 = wx1 * wy0, w11 = wx1 * f1;
-                    if (!__any_sync(FULL, dup)) {
-                        rmw4<O01, O10, O11>(s, act, w00, w01, w10, w11, wz0);
+                    const float2 wx = make_float2(wx0, wx1);
+                    const float2 wy1 = __fmul2_rn(wx, make_float2(f1, f1));           // (x0y1, x1y1)
+                    const float2 wy0 = __ffma2_rn(wy1, make_float2(-1.f, -1.f), wx);  // (x0y0, x1y0)
+                    const float wz0 = 1.f - f2;
+                    if (__builtin_expect(!__any_sync(FULL, dup), 1)) {
+                        float* const se = (float*)__cvta_shared_to_generic(act ? sb : ((sb & 0x7cu) | dummy_b));
+                        rmw4<O10, O01, O11>(se, wy0, wy1, wz0);
                         __syncwarp();
-                        rmw4<O01, O10, O11>(s + OZ, act, w00, w01, w10, w11, f2);
+                        rmw4<O10, O01, O11>(se + OZ, wy0, wy1, f2);
                         __syncwarp();
                     } else {
                         // rare (W_z < 1 makes two adjacent lanes share a z cell ~ once per 1/(1-W_z) samples):
                         // lanes flagged dup go in a second pass
 #pragma unroll 1
                         for (int pass = 0; pass < 2; ++pass) {
-                            const bool go = act && (dup == (pass == 1));
-                            rmw4<O01, O10, O11>(s, go, w00, w01, w10, w11, wz0);
+                            float* const se = (float*)__cvta_shared_to_generic(
+                                (act && (dup == (pass == 1))) ? sb : ((sb & 0x7cu) | dummy_b));
+                            rmw4<O10, O01, O11>(se, wy0, wy1, wz0);
                             __syncwarp();
-                            rmw4<O01, O10, O11>(s + OZ, go, w00, w01, w10, w11, f2);
+                            rmw4<O10, O01, O11>(se + OZ, wy0, wy1, f2);
                             __syncwarp();
                         }
                     }
-                    // advance one sample: one-sided carries, immediate strides
+                    // advance one sample: one-sided carries, the strides folded into one address increment
                     ++k;
                     f0 += tv.df[0]; f1 += tv.df[1]; f2 += tv.df[2];
-                    s += stepoff;
-                    if (f0 >= 1.0f) { f0 -= 1.0f; s += STX; }
-                    if (f1 >= 1.0f) { f1 -= 1.0f; s += STY; }
-                    if (f2 >= 1.0f) { f2 -= 1.0f; s += STZ; }
+                    int inc = stepoff;
+                    if (f0 >= 1.0f) { f0 -= 1.0f; inc = stepx; }
+                    if (f1 >= 1.0f) { f1 -= 1.0f; inc += STY; }
+                    if (f2 >= 1.0f) { f2 -= 1.0f; inc += STZ; }
+                    sb += 4u * (unsigned)inc;
                 }
             }
         }
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(TNW * 32)
 adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int ntz)
 {
     constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
-    extern __shared__ float smem_raw[];                  // guard | [TSX][TSY][TSZ] | guard
+    extern __shared__ __align__(128) float smem_raw[];   // guard | [TSX][TSY][TSZ] | guard
     float* const acc = smem_raw + TGUARD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int bb = blockIdx.x;
