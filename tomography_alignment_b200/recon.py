@@ -182,8 +182,41 @@ class CGLS(_DeviceSolver):
         return self._result(self.rms_error, k)
 
 
+def soft_thresholding(x, _lambda):
+    """recon/regularized.py:433-441: sgn(x) max(|x| - lambda, 0) (torch tensor in, torch tensor out)."""
+    return torch.sign(x) * torch.clamp(x.abs() - _lambda, min=0.0)
+
+
+def scalar_search_armijo(phi, phi0, derphi0, c1=1e-4, alpha0=1.0, amin=0.0):
+    """The interpolating Armijo search behind scipy.optimize's ``line_search_armijo`` (Nocedal & Wright,
+    Numerical Optimization, section 3.5: quadratic, then cubic interpolation), which recon/regularized.py:188
+    calls.  Returns (alpha, phi(alpha)) or (None, phi) when no acceptable step larger than ``amin`` exists."""
+    phi_a0 = phi(alpha0)
+    if phi_a0 <= phi0 + c1 * alpha0 * derphi0:
+        return alpha0, phi_a0
+    alpha1 = -derphi0 * alpha0 ** 2 / 2.0 / (phi_a0 - phi0 - derphi0 * alpha0)
+    phi_a1 = phi(alpha1)
+    if phi_a1 <= phi0 + c1 * alpha1 * derphi0:
+        return alpha1, phi_a1
+    while alpha1 > amin:
+        factor = alpha0 ** 2 * alpha1 ** 2 * (alpha1 - alpha0)
+        a = alpha0 ** 2 * (phi_a1 - phi0 - derphi0 * alpha1) - alpha1 ** 2 * (phi_a0 - phi0 - derphi0 * alpha0)
+        a = a / factor
+        b = -alpha0 ** 3 * (phi_a1 - phi0 - derphi0 * alpha1) + alpha1 ** 3 * (phi_a0 - phi0 - derphi0 * alpha0)
+        b = b / factor
+        alpha2 = (-b + np.sqrt(abs(b ** 2 - 3 * a * derphi0))) / (3.0 * a)
+        phi_a2 = phi(alpha2)
+        if phi_a2 <= phi0 + c1 * alpha2 * derphi0:
+            return alpha2, phi_a2
+        if (alpha1 - alpha2) > alpha1 / 2.0 or (1 - alpha2 / alpha1) < 0.96:
+            alpha2 = alpha1 / 2.0
+        alpha0, alpha1, phi_a0, phi_a1 = alpha1, alpha2, phi_a1, phi_a2
+    return None, phi_a1
+
+
 class RegularizedRecon(_DeviceSolver):
-    """recon/regularized.py:13-154 on the device: FISTA with a TV proximal step (``run_fista``).
+    """recon/regularized.py:13-441 on the device: FISTA with a TV proximal step (``run_fista``), Tikhonov
+    gradient descent (``run_tikhonov_gd``) and the two Lasso loops (``run_lasso_ista``, ``run_lasso_accelerated``).
     u_k = prox_{gamma g}(x_{k-1} + gamma A^T (b - A x_{k-1})); x_k = u_k + (t_{k-1} - 1)/t_k (u_k - u_{k-1}), gamma = 1/hyper;
     the prox is tv_denoise.denoise_fista(weight = gamma * beta_tv, niter = niter_tv) (regularized.py:84-103).
     With ``group`` the views are sharded and the backprojection all-reduced like recon/regularized_mpi.py:110-116;
@@ -228,3 +261,110 @@ class RegularizedRecon(_DeviceSolver):
                     print('semi-convergence criterion reached: stopping at k %3d with RMSE = %4.5f' % (k, rms_error[k]))
             k += 1
         return self.rec.cpu().numpy().astype(self.precision, copy=False), rms_error[:k]
+
+    # ---- shared bookkeeping of the three loops below (regularized.py:204-214, 290-299, 381-392) ----
+    def _track(self, k, res_norm, rms_error, convergence, first_check=1):
+        convergence[k] = res_norm
+        if self.ground_truth is None:
+            rms_error[k] = convergence[k] / self.norm_factor
+        else:
+            rms_error[k] = float(torch.linalg.vector_norm((self.ground_truth - self.rec).double())) / self.norm_factor
+        if k > first_check and rms_error[k] > rms_error[k - 1]:
+            if self.rank == 0:
+                print('semi-convergence criterion reached: stopping at k %3d with RMSE = %4.5f' % (k, rms_error[k]))
+            return 1
+        return 0
+
+    def _flat_result(self, rms_error, k, reshape):
+        rec = self.rec.cpu().numpy().astype(self.precision, copy=False)
+        if reshape:
+            rec = rec.reshape(tuple(int(v) for v in self.geometry.vox_shape))
+        return rec, rms_error[:k]
+
+    def run_tikhonov_gd(self, niter=100, reg_param=1.0, positivity=False, make_plot=False):
+        """regularized.py:156-237: x* = argmin 0.5|Ax - b|^2 + 0.5 lambda |x|^2 by gradient descent with the Armijo
+        search of scipy (``line_search_armijo``, alpha0 = 1).
+
+        The objective along the search direction is a quadratic in alpha, so it is evaluated from six inner
+        products and ONE extra forward projection A g per iteration instead of one projection per trial step
+        (the reference calls ``my_tikh_f`` per trial; that helper subtracts a 2-D array from a flat one and only
+        runs for n_proj = 1, the intended flat residual is what is restated here).  Returns (rec flat, rms_error),
+        like the reference."""
+        rms_error, convergence = np.zeros(niter, ), np.zeros(niter, )
+        stop, k = 0, 0
+        while k < niter and not stop:
+            res = self.projections - self._A(self.rec)                     # b - A x
+            grad = -self._At(res) + reg_param * self.rec                   # A^T (A x - b) + lambda x
+            Ag = self._A(grad)
+            rr = float(self._sum((res.double() ** 2).sum()))
+            rAg = float(self._sum((res.double() * Ag.double()).sum()))
+            AgAg = float(self._sum((Ag.double() ** 2).sum()))
+            xx = float((self.rec.double() ** 2).sum())
+            xg = float((self.rec.double() * grad.double()).sum())
+            gg = float((grad.double() ** 2).sum())
+            # f(x - a g) = 0.5 |res + a A g|^2 + 0.5 lambda |x - a g|^2
+            phi = lambda a: 0.5 * (rr + 2 * a * rAg + a * a * AgAg) + 0.5 * reg_param * (xx - 2 * a * xg + a * a * gg)
+            cost = 0.5 * (rr + reg_param * xx)
+            alpha, _ = scalar_search_armijo(phi, cost, -gg, alpha0=1.0)
+            if alpha is None:
+                print('line search failed at iteration %3d' % (k))
+                break
+            self.rec = self.rec - alpha * grad
+            if positivity:
+                self.rec.clamp_(min=0.0)
+            stop = self._track(k, np.sqrt(rr), rms_error, convergence)
+            k += 1
+        return self._flat_result(rms_error, k, reshape=False)
+
+    def _backtrack_lasso(self, t, beta, g0, dg0, _lambda):
+        """regularized.py:317-332: shrink t until g(x+) <= g(x) - <grad g, G_t> + |G_t|^2 / (2 t), G_t = x - x+."""
+        g0 = 0.5 * float(self._sum((g0.double() ** 2).sum()))
+        xp = self.rec
+        while t > 1.e-16:
+            xp = soft_thresholding(self.rec - t * dg0, t * _lambda)
+            Gt = (self.rec - xp).double()
+            g = 0.5 * float(self._sum(((self._A(xp) - self.projections).double() ** 2).sum()))
+            gp = g0 - float((dg0.double() * Gt).sum()) + (0.5 / t) * float((Gt ** 2).sum())
+            if g <= gp:
+                return xp, t, True
+            t *= beta
+        return xp, t, False
+
+    def run_lasso_ista(self, niter=100, reg_param=1.0, alpha0=1.0, beta=0.5, make_plot=False):
+        """regularized.py:239-315: proximal gradient descent for 0.5|Ax - b|^2 + lambda |x|_1 with backtracking;
+        the step sizes are kept in ``self.step_size`` (the reference plots them)."""
+        rms_error, convergence = np.zeros(niter, ), np.zeros(niter, )
+        self.step_size = np.zeros(niter, )
+        stop, k = 0, 0
+        while k < niter and not stop:
+            res = self._A(self.rec) - self.projections
+            grad = self._At(res)
+            _, alpha, success = self._backtrack_lasso(alpha0, beta, res, grad, reg_param)
+            self.step_size[k] = alpha
+            if not success:
+                print('line search failed to converge')
+                break
+            self.rec = soft_thresholding(self.rec - alpha * grad, alpha * reg_param)
+            stop = self._track(k, float(torch.sqrt(self._sum((res.double() ** 2).sum()))), rms_error, convergence)
+            k += 1
+        return self._flat_result(rms_error, k, reshape=True)
+
+    def run_lasso_accelerated(self, niter=100, reg_param=1.0, alpha0=1.0, beta=0.5, make_plot=False):
+        """regularized.py:334-413: the accelerated variant, v = x_1 + (k - 2)/(k + 1) (x_1 - x_0) with the step found by
+        the same backtracking at the current iterate.  Returns (rec flat, rms_error), like the reference."""
+        rms_error, convergence = np.zeros(niter, ), np.zeros(niter, )
+        x_0, x_1 = torch.zeros_like(self.rec), torch.zeros_like(self.rec)
+        stop, k = 0, 0
+        while k < niter and not stop:
+            res = self._A(self.rec) - self.projections
+            grad = self._At(res)
+            _, alpha, success = self._backtrack_lasso(alpha0, beta, res, grad, reg_param)
+            if not success:
+                print('line search failed to converge')
+                break
+            v = x_1 + (k - 2) / (k + 1) * (x_1 - x_0)
+            self.rec = soft_thresholding(v - alpha * grad, alpha * reg_param)
+            x_0, x_1 = x_1, self.rec.clone()
+            stop = self._track(k, float(torch.sqrt(self._sum((res.double() ** 2).sum()))), rms_error, convergence)
+            k += 1
+        return self._flat_result(rms_error, k, reshape=False)
