@@ -28,5 +28,6 @@ def t(fn, reps=3):
 out = {"lib": os.path.basename(os.environ.get("TOMO_B200_LIB", "default")), "n": n, "views": n_proj}
 if "f" in which: out["fwd_ms"] = t(lambda: be.forward(vol, out=proj))
 if "b" in which: out["back_ms"] = t(lambda: be.adjoint(y, out=bp))
+if "v" in which: out["voxback_ms"] = t(lambda: be.voxel_back(y, out=bp))
 if "g" in which: out["grad_ms"] = t(lambda: be.proj_grad(vol, meas=y, want_proj=False, want_dproj=False, repad=False))
 print(json.dumps(out))

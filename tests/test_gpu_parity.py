@@ -118,6 +118,37 @@ def test_voxel_driven_bilinear_backprojector(shape, dshape, n_proj, kw):
     assert rel_l2(be.voxel_back(torch.as_tensor(y)).cpu().numpy(), ref) <= TOL_PROJ
 
 
+VOXBACK_TMA_CASES = [
+    # (volume, detector, n_proj, make_geoms kwargs, pose kwargs, origin offset)
+    ((40, 36, 52), (48, 56), 7, dict(), dict(tilt=0.02, shift=2.0), None),                 # partial bricks, all views staged by TMA
+    ((32, 32, 64), (64, 72), 6, dict(), dict(tilt=0.0, shift=0.0, phis=[0.0, np.pi / 2, np.pi, 0.3, 1.0, 2.2]), None),  # exact lattice hits
+    ((48, 40, 40), (40, 44), 6, dict(), dict(tilt=0.3, shift=9.0), None),                  # big tilts: some views exceed the box -> plain kernel adds them
+    ((36, 36, 36), (56, 60), 5, dict(vox_pix=[1.3, 0.8, 1.1]), dict(tilt=0.05, shift=3.0), None),   # anisotropic voxels
+    ((40, 40, 40), (40, 48), 5, dict(), dict(tilt=0.02, shift=25.0), [7.5, 0.0, -11.25]),  # footprints leave the detector: TMA zero fill = bounds checks
+    ((24, 24, 40), (44, 42), 4, dict(), dict(tilt=0.02, shift=1.0), None),                 # ndz % 4 != 0: the plain kernel alone
+]
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,gkw,pkw,dorg", VOXBACK_TMA_CASES)
+def test_voxel_driven_backprojector_tma_staged(shape, dshape, n_proj, gkw, pkw, dorg):
+    """tomo_back_voxel_bilinear at sizes where the TMA-staged kernel runs (detector >= 32 x 44, ndz % 4 == 0): brick footprints,
+    zero fill outside the detector, views too tilted for the staged box, accumulate flag."""
+    g, og = make_geoms(shape, dshape, n_proj, **gkw)
+    phi, alpha, beta, xyz = random_poses(n_proj, 17, **pkw)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    y = np.random.default_rng(3).random((n_proj,) + tuple(dshape)).astype(np.float32)
+    origin = None if dorg is None else np.asarray(og.det_orig, dtype=np.float64) + np.asarray(dorg)
+    ref = O.voxel_back_project(og, y, alpha, beta, phi, xyz, origin=origin)
+    got = be.voxel_back(torch.as_tensor(y), origin=origin)
+    assert rel_l2(got.cpu().numpy(), ref) <= TOL_PROJ
+    # accumulate into an existing volume, and bitwise reproducibility
+    base = torch.full(tuple(shape), 0.25, dtype=torch.float32, device="cuda")
+    acc = be.voxel_back(torch.as_tensor(y), origin=origin, out=base.clone(), accumulate=True)
+    assert rel_l2(acc.cpu().numpy(), ref.reshape(shape) + 0.25) <= TOL_PROJ
+    assert torch.equal(got, be.voxel_back(torch.as_tensor(y), origin=origin))
+
+
 def test_reference_numpy_golden_fixtures():
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_numpy_cases.npz"))
     for name in gold["case_names"]:
@@ -308,6 +339,29 @@ def test_device_resident_sirt_and_cgls_on_gpu():
     c = CGLS(g, b, angles, xyz, options={"ground_truth": truth}, device="cuda:0")
     rec_c, err_c = c.run_main_iteration(niter=10)
     assert err_c[-1] < err[9]            # CGLS converges faster than SIRT per iteration
+
+
+def test_device_resident_tikhonov_and_lasso_on_gpu():
+    """recon.RegularizedRecon.run_tikhonov_gd / run_lasso_ista / run_lasso_accelerated on the GPU: the same iterates as the
+    CPU emulation of the same kernels (the host loops are checked against recon/regularized.py in the CPU tier)."""
+    from tomography_alignment_b200.recon import RegularizedRecon
+    n, n_proj = 24, 12
+    g, og = make_geoms((n, n, n), (n, n), n_proj)
+    phi, alpha, beta, xyz = benchmark_poses(n_proj)
+    angles = np.array([phi, alpha, beta]).T
+    truth = shepp3d(n)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(angles, xyz, g.cor_shift))
+    b = be.forward(torch.as_tensor(truth)).cpu().numpy().reshape(n_proj, -1)
+    for name, kw in (("run_tikhonov_gd", dict(niter=4, reg_param=0.2)), ("run_lasso_ista", dict(niter=3, reg_param=0.01)),
+                     ("run_lasso_accelerated", dict(niter=3, reg_param=0.01))):
+        gpu = RegularizedRecon(g, b, angles, xyz, options={"ground_truth": truth}, device="cuda:0")
+        emu = RegularizedRecon(g, b, angles, xyz, options={"ground_truth": truth}, backend=EmuBackend(g))
+        rec, err = getattr(gpu, name)(**kw)
+        rec_e, err_e = getattr(emu, name)(**kw)
+        assert len(err) == len(err_e) and err[-1] < 1.0, name
+        assert rel_l2(rec.ravel(), rec_e.ravel()) < 5e-5, name
+        np.testing.assert_allclose(err, err_e, rtol=1e-4, err_msg=name)
 
 
 def test_batched_alignment_recovers_jitter_on_gpu():

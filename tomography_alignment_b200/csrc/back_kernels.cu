@@ -31,9 +31,17 @@
 //     exactly the reference's terms, in a fixed order: results are bitwise reproducible.
 // (2) voxel_bilinear_kernel: the orphan voxel-driven backprojector of src/back_projection.f90 /
 //     src/external_back_projection.f90 (inverse pose convention, 4 bilinear taps, y ignored).
+// (2b) voxel_bilinear_tma_kernel: the same operator with the projection tile of every view staged in shared
+//     memory by TMA.  A block owns a 16 x 16 x 32 voxel brick (32 accumulators per thread, lanes along z) for
+//     the whole launch; one thread computes the brick's detector footprint per view and issues one
+//     cp.async.bulk.tensor (3-D map {z', x', view}, box 44 x 32 x 1, z' start a multiple of 4) into a 4-stage ring of mbarriers, so the
+//     loads of the next views overlap the interpolation of the current one.  Out-of-detector parts of the box
+//     are zero-filled by the TMA unit, which IS the reference's per-tap bounds check.  No atomics, each voxel
+//     written once, bitwise reproducible.
 //
 // Lanes run along z, which is contiguous in the volume and (for small tilts) maps to iz, which is
 // contiguous in the projections, so both sides are coalesced.
+#include <cuda.h>            // CUtensorMap types; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
 #include <cuda_runtime.h>
 #include "tomo_common.h"
 #include "back_core.h"
@@ -49,6 +57,7 @@ struct BackArgs {
     int nx, ny, nz, ndx, ndz, n_proj, accumulate;
     int only_uncoloured;     // gather kernel: visit only the views the tile kernel skipped (V_NCOL == 0)
     int skip_separable;      // leave views with V_SEP == 1 to the separable adjoint (workspace variant)
+    int only_vbig;           // voxel_bilinear: visit only the views the TMA kernel skipped (V_VBOK == 0)
     double origin[3];        // voxel_bilinear only: the Fortran's origin argument
     double vox0[3], vpix[3]; // voxel_bilinear only: physical voxel centres = vox0 + idx*vpix
 };
@@ -81,15 +90,163 @@ voxel_bilinear_kernel(const BackArgs A)
     const int x = blockIdx.z * BX + threadIdx.z;
     if (x >= A.nx || y >= A.ny || z >= A.nz) return;
     const size_t n_det = (size_t)A.ndx * A.ndz;
+    if (A.only_vbig && A.views[V_NVBIG] == 0.0) return;             // every record holds the table's count
     const double cx = A.vox0[0] + x * A.vpix[0], cy = A.vox0[1] + y * A.vpix[1], cz = A.vox0[2] + z * A.vpix[2];
     float acc = 0.f;
-    for (int view = 0; view < A.n_proj; ++view)
-        acc += voxel_bilinear_view(A.proj + (size_t)view * n_det, A.views + (size_t)view * TOMO_VIEW_STRIDE,
-                                   A.ndx, A.ndz, A.origin, cx, cy, cz);
+    for (int view = 0; view < A.n_proj; ++view) {
+        const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+        if (A.only_vbig && V[V_VBOK] != 0.0) continue;
+        acc += voxel_bilinear_view(A.proj + (size_t)view * n_det, V, A.ndx, A.ndz, A.origin, cx, cy, cz);
+    }
     const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
     A.vol[vi] = A.accumulate ? A.vol[vi] + acc : acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// (2b) TMA-staged voxel-driven backprojector
+constexpr int VBX = TOMO_VB_X, VBY = TOMO_VB_Y, VBZ = TOMO_VB_Z;     // voxel brick of a block
+constexpr int VTX = TOMO_VB_TX, VTZ = TOMO_VB_TZ;                    // staged detector box: VTX rows (x') of VTZ pixels (z')
+constexpr int VB_WARPS = 8, VB_STAGES = 4;
+constexpr int VB_YPW = VBY / VB_WARPS;                               // y rows of the brick per warp
+constexpr unsigned VB_TILE_BYTES = VTX * VTZ * sizeof(float);
+static_assert(VBZ == 32 && VBY % VB_WARPS == 0 && (VTZ * sizeof(float)) % 16 == 0, "brick / box shape");
+
+struct VbStage { float ux0, uz0, a00, a01, a02, a20, a21, a22; };   // per (brick, view) constants written by the producer
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(VB_WARPS * 32)
+voxel_bilinear_tma_kernel(const BackArgs A, const __grid_constant__ CUtensorMap tmap)
+{
+    __shared__ __align__(128) float tile[VB_STAGES][VTX * VTZ];
+    __shared__ VbStage hdr[VB_STAGES];
+    __shared__ __align__(8) unsigned long long full[VB_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.z * VBX, y0 = blockIdx.y * VBY, z0 = blockIdx.x * VBZ;
+    const unsigned tile_b = (unsigned)__cvta_generic_to_shared(&tile[0][0]);
+    const unsigned full_b = (unsigned)__cvta_generic_to_shared(&full[0]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VB_STAGES; ++s) mbar_init(full_b + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- producer (thread 0): footprint of the brick under the next staged view, then one TMA load ----
+    int next_view = 0;
+    auto issue = [&](int stage) {
+        while (next_view < A.n_proj && A.views[(size_t)next_view * TOMO_VIEW_STRIDE + V_VBOK] == 0.0) ++next_view;
+        if (next_view >= A.n_proj) return;
+        const double* __restrict__ V = A.views + (size_t)next_view * TOMO_VIEW_STRIDE;
+        const double c0[3] = {A.vox0[0] + x0 * A.vpix[0], A.vox0[1] + y0 * A.vpix[1], A.vox0[2] + z0 * A.vpix[2]};
+        const int ext[3] = {VBX - 1, VBY - 1, VBZ - 1};
+        double u0[2], umin[2], a[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = 2 * r;                                           // x' (row 0) and z' (row 2) of Ry Rx Rz
+            u0[r] = V[V_VROT + 3 * row] * c0[0] + V[V_VROT + 3 * row + 1] * c0[1] + V[V_VROT + 3 * row + 2] * c0[2]
+                    + V[V_VTR + row] - A.origin[row];
+            umin[r] = u0[r];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                a[r][k] = V[V_VROT + 3 * row + k] * A.vpix[k];
+                umin[r] += fmin(0.0, a[r][k] * ext[k]);
+            }
+        }
+        // box origin; clamped far outside the detector (an all-zero box) so the int conversion is defined.  The z' start is
+        // rounded down to a multiple of 4: the TMA unit faults on a start that is not 16-byte aligned along the inner dimension
+        const double ox = floor(fmin(fmax(umin[0] - 1e-3, -1.0e6), 1.0e6));
+        const double oz = 4.0 * floor(0.25 * fmin(fmax(umin[1] - 1e-3, -1.0e6), 1.0e6));
+        VbStage h;
+        h.ux0 = (float)(fmin(fmax(u0[0] - ox, -1.0e6), 1.0e6) - 0.5); h.uz0 = (float)(fmin(fmax(u0[1] - oz, -1.0e6), 1.0e6) - 0.5);
+        h.a00 = (float)a[0][0]; h.a01 = (float)a[0][1]; h.a02 = (float)a[0][2];
+        h.a20 = (float)a[1][0]; h.a21 = (float)a[1][1]; h.a22 = (float)a[1][2];
+        hdr[stage] = h;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of this stage vs the async write
+        mbar_expect_tx(full_b + 8u * stage, VB_TILE_BYTES);
+        tma_load_3d(tile_b + VB_TILE_BYTES * stage, &tmap, full_b + 8u * stage, (int)oz, (int)ox, next_view);
+        ++next_view;
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < VB_STAGES; ++s) issue(s);
+
+    float acc[VB_YPW * VBX];
+#pragma unroll
+    for (int i = 0; i < VB_YPW * VBX; ++i) acc[i] = 0.f;
+
+    // floor by magic number: t = (u - 0.5) + 1.5 * 2^23 rounds u - 0.5 to the nearest integer n = floor(u) and leaves n
+    // in the low mantissa bits; on an exact tie either neighbour cell gives the same bilinear value (weight 0 / 1).
+    constexpr float MAGIC = 12582912.0f;
+    const float fl = (float)lane;
+    int cnt = 0;
+    for (int view = 0; view < A.n_proj; ++view) {
+        if (A.views[(size_t)view * TOMO_VIEW_STRIDE + V_VBOK] == 0.0) continue;      // block-uniform; the plain kernel adds it
+        const int stage = cnt % VB_STAGES;
+        mbar_wait(full_b + 8u * stage, (unsigned)((cnt / VB_STAGES) & 1));
+        const VbStage h = hdr[stage];
+        const unsigned basec = tile_b + VB_TILE_BYTES * stage;       // shared byte address of box cell (0, 0)
+        const float bxz = fmaf(fl, h.a02, h.ux0), bzz = fmaf(fl, h.a22, h.uz0);
+#pragma unroll
+        for (int yy = 0; yy < VB_YPW; ++yy) {
+            const float fy = (float)(warp * VB_YPW + yy);
+            const float uxy = fmaf(fy, h.a01, bxz), uzy = fmaf(fy, h.a21, bzz);
+#pragma unroll
+            for (int xx = 0; xx < VBX; ++xx) {
+                const float ux = fmaf((float)xx, h.a00, uxy), uz = fmaf((float)xx, h.a20, uzy);   // u - 0.5, box-local
+                const float tx = ux + MAGIC, tz = uz + MAGIC;
+                const float dx = ux - (tx - MAGIC), dz = uz - (tz - MAGIC);                       // frac - 0.5
+                const float ax = 0.5f + dx, wx0 = 0.5f - dx, az = 0.5f + dz, wz0 = 0.5f - dz;
+                const unsigned off = (__float_as_uint(tx) & 0xffu) * (unsigned)VTZ + (__float_as_uint(tz) & 0xffu);
+                const float* __restrict__ t = (const float*)__cvta_shared_to_generic(basec + 4u * off);
+                const float lo = fmaf(t[1], az, t[0] * wz0), hi = fmaf(t[VTZ + 1], az, t[VTZ] * wz0);
+                acc[yy * VBX + xx] = fmaf(hi, ax, fmaf(lo, wx0, acc[yy * VBX + xx]));
+            }
+        }
+        __syncthreads();                                   // every thread is done with this stage
+        if (threadIdx.x == 0) issue(stage);
+        ++cnt;
+    }
+
+    const int z = z0 + lane;
+    if (z < A.nz) {
+#pragma unroll
+        for (int yy = 0; yy < VB_YPW; ++yy) {
+            const int y = y0 + warp * VB_YPW + yy;
+#pragma unroll
+            for (int xx = 0; xx < VBX; ++xx) {
+                const int x = x0 + xx;
+                if (x < A.nx && y < A.ny) {
+                    const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
+                    A.vol[vi] = A.accumulate ? A.vol[vi] + acc[yy * VBX + xx] : acc[yy * VBX + xx];
+                }
+            }
+        }
+    }
+}
 
 constexpr int TNW = TOMO_BT_WARPS;     // warps per block of the tile kernel
 // Shared-memory tile: one ghost cell per side, [TSX][TSY][TSZ] with TSZ = 32 so that lanes that straddle two
@@ -380,7 +537,7 @@ static int fill_back(const TomoGeom* g, const void* views, int n_proj, const flo
     if (!g || !views || !proj || !vol || n_proj <= 0) { tomo_set_error("backprojector: null pointer or n_proj <= 0"); return TOMO_E_ARG; }
     A->proj = proj; A->views = (const double*)views; A->vol = vol;
     A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz;
-    A->n_proj = n_proj; A->accumulate = accumulate; A->only_uncoloured = 0; A->skip_separable = 0;
+    A->n_proj = n_proj; A->accumulate = accumulate; A->only_uncoloured = 0; A->skip_separable = 0; A->only_vbig = 0;
     for (int a = 0; a < 3; ++a) { A->origin[a] = 0.0; A->vox0[a] = g->vox_origin[a]; A->vpix[a] = g->vox_pix[a]; }
     *grid = dim3((g->nz + BZ - 1) / BZ, (g->ny + BY - 1) / BY, (g->nx + BX - 1) / BX);
     if (grid->y > 65535u || grid->z > 65535u) { tomo_set_error("backprojector: volume too large for the launch grid"); return TOMO_E_RANGE; }
@@ -449,6 +606,37 @@ extern "C" int tomo_back_adjoint_ws(const TomoGeom* g, const void* views, int n_
     return back_adjoint_impl(g, views, n_proj, proj, vol, accumulate, workspace, workspace_bytes, stream);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library does not link libcuda).
+typedef CUresult (*TomoEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TomoEncodeTiled tomo_encode_tiled()
+{
+    static TomoEncodeTiled fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (TomoEncodeTiled)p;
+    }();
+    return fn;
+}
+
+// 3-D tensor map {z', x', view} over the projections with the box the TMA kernel stages; false when the layout
+// does not meet the TMA constraints (16-byte aligned base and row pitch) or the detector is smaller than the box.
+static bool voxback_tensor_map(const TomoGeom* g, int n_proj, const float* proj, CUtensorMap* map)
+{
+    if (g->ndz % 4 != 0 || ((uintptr_t)proj & 15u) != 0 || g->ndz < VTZ || g->ndx < VTX) return false;
+    TomoEncodeTiled enc = tomo_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)g->ndz, (cuuint64_t)g->ndx, (cuuint64_t)n_proj};
+    const cuuint64_t strides[2] = {(cuuint64_t)g->ndz * sizeof(float), (cuuint64_t)g->ndz * g->ndx * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)VTZ, (cuuint32_t)VTX, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)proj, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int tomo_back_voxel_bilinear(const TomoGeom* g, const void* views, int n_proj,
                                         const double origin[3], const float* proj, float* vol,
                                         int accumulate, void* stream)
@@ -457,6 +645,14 @@ extern "C" int tomo_back_voxel_bilinear(const TomoGeom* g, const void* views, in
     if (!origin) { tomo_set_error("tomo_back_voxel_bilinear: origin is NULL"); return TOMO_E_ARG; }
     if (int e = fill_back(g, views, n_proj, proj, vol, accumulate, &A, &grid)) return e;
     for (int a = 0; a < 3; ++a) A.origin[a] = origin[a];
+    CUtensorMap map;
+    const dim3 bricks((g->nz + VBZ - 1) / VBZ, (g->ny + VBY - 1) / VBY, (g->nx + VBX - 1) / VBX);
+    if (bricks.y <= 65535u && bricks.z <= 65535u && voxback_tensor_map(g, n_proj, proj, &map)) {
+        // views whose brick footprint fits the staged box (V_VBOK), then the rest through the plain kernel
+        voxel_bilinear_tma_kernel<<<bricks, VB_WARPS * 32, 0, (cudaStream_t)stream>>>(A, map);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "voxel_bilinear_tma_kernel")) return e;
+        A.accumulate = 1; A.only_vbig = 1;
+    }
     voxel_bilinear_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A);
     return tomo_check_cuda(cudaGetLastError(), "voxel_bilinear_kernel");
 }

@@ -34,7 +34,10 @@ enum {
     V_SEP  = 146,  // 1   1.0 when the view has no tilt (alpha = beta = 0 exactly): W_x = W_y = U_z = D_z = 0, so z decouples
                    //     from (x, y) and the separable kernels apply
     V_NSEP = 147,  // 1   number of views of the whole table with V_SEP == 1 (same in every record)
-    V_END  = 148
+    V_VBOK = 148,  // 1   1.0 when the detector footprint of a TOMO_VB_X x _Y x _Z voxel brick under the voxel-driven
+                   //     transform fits the TOMO_VB_TX x TOMO_VB_TZ box the TMA-staged backprojector loads per view
+    V_NVBIG = 149, // 1   number of views of the whole table with V_VBOK == 0 (same in every record)
+    V_END  = 150
 };
 
 static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");
@@ -60,3 +63,12 @@ int tomo_nzp(int nz) { return ((nz + 2 * TOMO_PAD + 31) / 32) * 32; }
 #ifndef TOMO_BT_WARPS
 #define TOMO_BT_WARPS 8      // warps per block of the tile kernel
 #endif
+
+// Voxel brick of the TMA-staged voxel-driven backprojector and the detector box (x' rows of z' pixels) it stages
+// per view; the host marks the views whose footprint fits (V_VBOK).  The box starts at a z' index that is a multiple of 4
+// (TMA needs a 16-byte aligned start along the innermost dimension), which costs up to 3 extra columns.
+#define TOMO_VB_X 16
+#define TOMO_VB_Y 16
+#define TOMO_VB_Z 32
+#define TOMO_VB_TX 32
+#define TOMO_VB_TZ 44

@@ -170,6 +170,18 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[V_VROT + 3 * i + j] = Vr.m[i][j];
         put(o + V_VTR, mul(Rb, t));
 
+        // footprint of a voxel brick on the detector under x' = Vr c + Ry t (detector index = x' - origin, pitch 1):
+        // the span of x' (row 0) and z' (row 2) over the brick's voxel centres, plus the two taps and the floor
+        {
+            const int B[3] = {TOMO_VB_X, TOMO_VB_Y, TOMO_VB_Z};
+            double sx = 0.0, sz = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                sx += std::fabs(Vr.m[0][a] * g->vox_pix[a]) * (B[a] - 1);
+                sz += std::fabs(Vr.m[2][a] * g->vox_pix[a]) * (B[a] - 1);
+            }
+            o[V_VBOK] = (sx + 3.01 <= TOMO_VB_TX && sz + 6.01 <= TOMO_VB_TZ) ? 1.0 : 0.0;     // + 3: box start rounded down to 4
+        }
+
         // derivative_rigid (utilities/voxel_utilities.py:23-48), rows x' (0) and z' (2) only -- the Fortran never
         // reads the y' row (src/vox_wt_grad.f90:27-29).  Each is affine in the voxel centre c:
         //   k = 0..2: R_b[:, k]                      (constant)
@@ -194,9 +206,12 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
     for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_NCOL] == 0.0) n_uncoloured += 1.0;
     double n_sep = 0.0;
     for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_SEP] != 0.0) n_sep += 1.0;
+    double n_vbig = 0.0;
+    for (int v = 0; v < n_proj; ++v) if (out[(size_t)v * TOMO_VIEW_STRIDE + V_VBOK] == 0.0) n_vbig += 1.0;
     for (int v = 0; v < n_proj; ++v) {
         out[(size_t)v * TOMO_VIEW_STRIDE + V_NUNCOL] = n_uncoloured;
         out[(size_t)v * TOMO_VIEW_STRIDE + V_NSEP] = n_sep;
+        out[(size_t)v * TOMO_VIEW_STRIDE + V_NVBIG] = n_vbig;
     }
     return 0;
 }
