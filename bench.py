@@ -342,6 +342,11 @@ def run_b200(a):
                 "gradient_frac_of_peak": bytes_g / (u_g * 1e-3) / 1e9 / peak,
                 "step_ms": u_f + u_b + u_g}
     log("untilted-pose timing done")
+    # secondary measurement: the voxel-driven bilinear backprojector (src/back_projection.f90), TMA-staged kernel
+    t_v = time_kernel(lambda: be.voxel_back(meas, out=bp))
+    voxel_driven = {"kernel": "voxel_bilinear_tma_kernel", "ms": t_v, "algorithmic_gbs": bytes_b / (t_v * 1e-3) / 1e9,
+                    "frac_of_peak": bytes_b / (t_v * 1e-3) / 1e9 / peak}
+    log("voxel-driven backprojector timing done")
 
     # end to end through the public API with pinned host buffers
     e2e = None
@@ -423,7 +428,7 @@ def run_b200(a):
                            "l2": "inputs exceed L2 (volume %d MiB, projections %d MiB per rank)"
                                  % (4 * n ** 3 // 2 ** 20, 4 * my_n * n * n // 2 ** 20),
                            "phantom": "shepp3d", "poses": "examples/generate_data.py jitter, seed 20240229"},
-                "roofline": roofline, "untilted_poses": untilted, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "untilted_poses": untilted, "voxel_driven_backprojector": voxel_driven, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "impl": "b200"}
         emit(line)
     if world > 1:

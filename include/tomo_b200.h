@@ -117,7 +117,11 @@ TOMO_API int tomo_back_adjoint_gather(const TomoGeom* geom, const void* views_de
  * (src/back_projection.f90:1-34, src/external_back_projection.f90:1-68): x' = Ry(b)(Rx(a)Rz(p)x + t),
  * 4 bilinear taps of the view's image at (x'_x - origin_x, x'_z - origin_z), y ignored.
  * NOT the transpose of tomo_forward (inverse pose convention).  origin[3] is the
- * Fortran's `origin` argument; det images use the [n_proj][ndx][ndz] layout above. */
+ * Fortran's `origin` argument; det images use the [n_proj][ndx][ndz] layout above.
+ * When ndz % 4 == 0, proj_dev is 16-byte aligned and the detector is at least 32 x 44 pixels the projection
+ * tile of every view is staged in shared memory by TMA (one 3-D tensor map over proj_dev, encoded per call on
+ * the host, no device allocation); other layouts and views tilted beyond the staged box take the plain gather
+ * kernel.  Both write every voxel exactly once (no atomics, bitwise reproducible). */
 TOMO_API int tomo_back_voxel_bilinear(const TomoGeom* geom, const void* views_dev, int n_proj,
                              const double origin[3], const float* proj_dev, float* vol_dev,
                              int accumulate, void* stream);
