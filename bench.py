@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--cpu-size", type=int, default=256, help="volume size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-phantom", action="store_true",
+                    help="build the phantom with numpy on the host (profiling runs: keeps torch's phantom kernels out of ncu launch lists)")
     return ap.parse_args()
 
 
@@ -210,7 +212,7 @@ def run_b200(a):
     be.set_poses(est[mine])
 
     # small phantoms are built on the host (keeps profiler launch lists free of phantom kernels)
-    vol_true = torch.as_tensor(shepp3d(n)).to(dev) if n <= 256 else shepp3d(n, device=dev)
+    vol_true = torch.as_tensor(shepp3d(n)).to(dev) if (n <= 256 or a.host_phantom) else shepp3d(n, device=dev)
     meas = be_true.forward(vol_true).clone()              # b = A_true phantom, (my_n, n, n)
     vol = (0.9 * vol_true).contiguous()                    # current reconstruction estimate
     proj = torch.empty_like(meas)
