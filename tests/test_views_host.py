@@ -70,3 +70,28 @@ def test_argument_errors_do_not_touch_cuda():
     assert L.tomo_back_adjoint(ctypes.byref(cg), None, 1, None, None, 0, None) == -1
     assert L.tomo_proj_grad(ctypes.byref(cg), None, 1, None, None, None, None, None, None, None, 0, None) == -1
     assert L.tomo_pad_volume(ctypes.byref(cg), None, None, None) == -1
+
+
+def test_kernel_selection_flags():
+    """Per-view flags the kernels dispatch on: separable (no tilt), tile-scatter colour count, TMA box fit of the
+    voxel-driven backprojector; the table-wide counts are replicated in every record (sub-tables stay valid)."""
+    NCOL, NUNCOL, SEP, NSEP, VBOK, NVBIG = 86, 87, 146, 147, 148, 149
+    n_proj = 6
+    g, og = make_geoms((32, 32, 32), (32, 32), n_proj)
+    phi = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.5])
+    alpha = np.array([0.0, 0.0, 0.01, -0.02, 0.1, 0.0])
+    beta = np.array([0.0, 0.0, 0.02, 0.01, 0.4, 1.5])          # view 4: z leaks into x' (box too narrow); last view: rays almost along z
+    views = views_for(g, pose_table(np.array([phi, alpha, beta]).T, np.zeros((n_proj, 3)), g.cor_shift))
+    assert list(views[:, SEP]) == [1, 1, 0, 0, 0, 0] and np.all(views[:, NSEP] == 2)
+    assert np.all(views[:4, NCOL] >= 2) and views[5, NCOL] == 0 and np.all(views[:, NUNCOL] == np.sum(views[:, NCOL] == 0))
+    # brick footprint: 16 x 16 x 32 voxels under Ry Rx Rz, box 32 x 44 with the z' start rounded down to a multiple of 4
+    for i in range(n_proj):
+        R = O.rot_y(beta[i]) @ O.rot_x(alpha[i]) @ O.rot_z(phi[i])
+        sx = np.abs(R[0]) @ np.array([15, 15, 31.0])
+        sz = np.abs(R[2]) @ np.array([15, 15, 31.0])
+        assert views[i, VBOK] == float(sx + 3.01 <= 32 and sz + 6.01 <= 44)
+    assert list(views[:, VBOK]) == [1, 1, 1, 1, 0, 0] and np.all(views[:, NVBIG] == 2)
+    # anisotropic voxels scale the footprint
+    g2, _ = make_geoms((32, 32, 32), (32, 32), 1, vox_pix=[2.5, 1.0, 1.0])
+    v2 = views_for(g2, pose_table(np.array([[0.0, 0.0, 0.0]]), np.zeros((1, 3)), g2.cor_shift))
+    assert v2[0, VBOK] == 0 and v2[0, NVBIG] == 1
