@@ -149,6 +149,26 @@ def test_voxel_driven_backprojector_tma_staged(shape, dshape, n_proj, gkw, pkw, 
     assert torch.equal(got, be.voxel_back(torch.as_tensor(y), origin=origin))
 
 
+def test_voxel_backprojector_tma_equals_plain_kernel_at_256():
+    """Size-independent check at 256^3 x 12 jittered views: the TMA-staged kernel (float32 box-local positions) against the
+    plain gather kernel (float64 positions per voxel), which the same call takes when the projections are not 16-byte aligned."""
+    n, n_proj = 256, 12
+    g, og = make_geoms((n, n, n), (n, n), n_proj)
+    phi, alpha, beta, xyz = benchmark_poses(n_proj)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    buf = torch.rand(n_proj * n * n + 1, device="cuda", generator=gen)
+    y_unaligned = buf[1:].view(n_proj, n, n)                  # base address = 4 mod 16: plain kernel
+    y_aligned = y_unaligned.clone()                           # fresh allocation: TMA kernel
+    assert y_unaligned.data_ptr() % 16 != 0 and y_aligned.data_ptr() % 16 == 0
+    v_tma = be.voxel_back(y_aligned)
+    v_plain = be.voxel_back(y_unaligned)
+    err = torch.linalg.vector_norm((v_tma - v_plain).double()) / torch.linalg.vector_norm(v_plain.double())
+    assert float(err) <= TOL_PROJ
+    assert float(v_plain.abs().max()) > 0
+
+
 def test_reference_numpy_golden_fixtures():
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_numpy_cases.npz"))
     for name in gold["case_names"]:
