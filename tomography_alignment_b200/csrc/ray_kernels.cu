@@ -28,6 +28,9 @@ constexpr int TILE_Z = 32;     // lanes: iz
 #define RAY_TILE_X 8
 #endif
 constexpr int TILE_X = RAY_TILE_X;      // warps: ix
+#ifndef RAY_BAND_TILES
+#define RAY_BAND_TILES 16
+#endif
 constexpr int NRED   = 7;      // 6 gradient components + cost
 
 struct RayArgs {
@@ -40,16 +43,24 @@ struct RayArgs {
     int nx, ny, nz, ndx, ndz, n_proj;
     int sxp, syp;            // padded strides (floats) of x and y; z stride is 1
     int nxt, nzt;            // detector tiles along x and z
+    int xparts, xpp;         // launch order: bands of xpp x-tiles (see ray_kernel_body)
     int skip_separable;      // leave views with V_SEP == 1 to the separable kernels
 };
 
 template <bool GRAD>
 __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
 {
-    const int bid  = blockIdx.x;
-    const int xt   = bid % A.nxt;
-    const int view = (bid / A.nxt) % A.n_proj;
-    const int zt   = bid / (A.nxt * A.n_proj);
+    // launch order: x-tile within a part fastest, then view, then part, then z-tile.  All views sweep over one z-slab
+    // restricted to one band of detector columns before the next band starts, so the working set in L2 is a band of the
+    // slab (which rotates slowly with the view angle) instead of the whole slab.
+    const int pb   = blockIdx.x;
+    const int xl   = pb % A.xpp;
+    const int view = (pb / A.xpp) % A.n_proj;
+    const int part = (pb / (A.xpp * A.n_proj)) % A.xparts;
+    const int zt   = pb / (A.xpp * A.n_proj * A.xparts);
+    const int xt   = part * A.xpp + xl;
+    if (xt >= A.nxt) return;                                       // block-uniform (last part may be ragged)
+    const int bid  = (zt * A.n_proj + view) * A.nxt + xt;          // logical tile id: layout of the block partials
     const int iz = zt * TILE_Z + threadIdx.x;
     const int ix = xt * TILE_X + threadIdx.y;
     const bool active = (ix < A.ndx) && (iz < A.ndz);
@@ -189,7 +200,11 @@ static int fill_args(const TomoGeom* g, const void* views, int n_proj, const flo
     A->sxp = (g->ny + 2 * TOMO_PAD) * A->syp;
     A->nxt = (g->ndx + TILE_X - 1) / TILE_X;
     A->nzt = (g->ndz + TILE_Z - 1) / TILE_Z;
-    const double nblocks = (double)A->nxt * A->nzt * n_proj;
+    // bands of about RAY_BAND_TILES x-tiles: 16 tiles = 128 detector columns keep a band of a 36-plane slab of a 512^2
+    // cross-section at ~12 MB (measured best on B200, profiles/README.md)
+    A->xparts = (A->nxt + RAY_BAND_TILES - 1) / RAY_BAND_TILES;
+    A->xpp = (A->nxt + A->xparts - 1) / A->xparts;
+    const double nblocks = (double)A->xpp * A->xparts * A->nzt * n_proj;
     if (nblocks >= 2147483647.0) { tomo_set_error("too many detector tiles for one launch"); return TOMO_E_RANGE; }
     return 0;
 }
@@ -203,7 +218,7 @@ extern "C" int tomo_forward(const TomoGeom* g, const void* views, int n_proj,
     A.proj = proj;
     A.skip_separable = 1;
     const dim3 block(TILE_Z, TILE_X);
-    ray_kernel_forward<<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+    ray_kernel_forward<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
     if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward")) return e;
     // untilted views (alpha = beta = 0): separable kernel; both kernels return at once for views of the other kind
     return tomo_forward_separable_launch(g, views, n_proj, volpad, proj, stream);
@@ -238,7 +253,7 @@ extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
     }
     A.skip_separable = 1;
     const dim3 block(TILE_Z, TILE_X);
-    ray_kernel_gradient<<<A.nxt * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+    ray_kernel_gradient<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
     if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_gradient")) return e;
     // untilted views: separable kernel with its own block partials behind the generic ones
     double* sep_partial = reduce ? A.partial + (size_t)NRED * A.nxt * A.nzt * n_proj : nullptr;

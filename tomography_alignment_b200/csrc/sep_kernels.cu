@@ -3,8 +3,8 @@
 // Block = 8 warps = 8 adjacent ix; a warp handles one ix and one chunk of SEP_CHUNK padded z planes, four planes per
 // lane with 128-bit loads (the 32 lanes of a warp read 512 contiguous bytes of each of the 4 (x, y) corner rows).  All
 // lanes of a warp share the (x, y) march, so there is no divergence.  The warp then stages S in shared memory and
-// applies the 2-tap z interpolation for the detector rows whose floor plane falls in its chunk.  The volume is
-// streamed once per view: this kernel is HBM/L2-bandwidth bound, not issue bound.
+// applies the 2-tap z interpolation for the detector rows whose floor plane falls in its chunk.  Blocks are launched
+// band by band (sep_item) so that the part of the volume a band of detector columns reads stays in L2 across views.
 #include <cuda_runtime.h>
 #include "tomo_common.h"
 #include "sep_core.h"
@@ -12,6 +12,30 @@
 namespace {
 
 constexpr int SEP_WARPS = 8;
+#ifndef SEP_BAND_TILES
+#define SEP_BAND_TILES 16      // launch order: bands of 16 x-tiles (128 detector columns), see sep_item()
+#endif
+
+// Launch order of the ray-driven separable kernels: x-tile within a band fastest, then view, then band, then z chunk.
+// All views sweep over one band of detector columns of one z chunk before the next band starts; the part of the chunk
+// a band touches rotates slowly with the view angle, so it stays in L2 instead of being streamed from HBM once per view.
+// Returns false for the padding blocks of a ragged last band.  `logical` is the (chunk, view, xt) id the partials use.
+__device__ __forceinline__ bool sep_item(long long pb, int nxt, int n_proj, int& xt, int& view, int& chunk, long long& logical)
+{
+    const int parts = (nxt + SEP_BAND_TILES - 1) / SEP_BAND_TILES, xpp = (nxt + parts - 1) / parts;
+    const int xl = (int)(pb % xpp);
+    view = (int)((pb / xpp) % n_proj);
+    const int part = (int)((pb / ((long long)xpp * n_proj)) % parts);
+    chunk = (int)(pb / ((long long)xpp * n_proj * parts));
+    xt = part * xpp + xl;
+    logical = ((long long)chunk * n_proj + view) * nxt + xt;
+    return xt < nxt;
+}
+__host__ inline double sep_grid_blocks(int nxt, int nchunk, int n_proj)
+{
+    const int parts = (nxt + SEP_BAND_TILES - 1) / SEP_BAND_TILES, xpp = (nxt + parts - 1) / parts;
+    return (double)xpp * parts * nchunk * n_proj;
+}
 
 struct SepArgs {
     const float*  volpad;
@@ -29,10 +53,8 @@ sep_forward_kernel(const SepArgs A)
     // one block per (chunk, view, x-tile) item (a persistent grid-stride loop measured 25 % slower); blocks of
     // tilted views return at once
     {
-    const long long item = blockIdx.x;
-    const int xt = (int)(item % A.nxt);
-    const int view = (int)((item / A.nxt) % A.n_proj);
-    const int chunk = (int)(item / ((long long)A.nxt * A.n_proj));
+    int xt, view, chunk; long long item;
+    if (!sep_item(blockIdx.x, A.nxt, A.n_proj, xt, view, chunk, item)) return;
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
     if (V[V_SEP] == 0.0) return;                                   // tilted view: the generic kernel does it
     const int ix = xt * SEP_WARPS + warp;
@@ -91,10 +113,8 @@ sep_gradient_kernel(const SepGradArgs A)
 {
     __shared__ float M[SEP_WARPS][6][SEP_CHUNK];
     __shared__ double red_sm[SEP_WARPS][7];
-    const long long item = blockIdx.x;
-    const int xt = (int)(item % A.nxt);
-    const int view = (int)((item / A.nxt) % A.n_proj);
-    const int chunk = (int)(item / ((long long)A.nxt * A.n_proj));
+    int xt, view, chunk; long long item;
+    if (!sep_item(blockIdx.x, A.nxt, A.n_proj, xt, view, chunk, item)) return;
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
     if (V[V_SEP] == 0.0) return;                                   // tilted view (block-uniform): ray_kernel_gradient does it
     const int lane = threadIdx.x, warp = threadIdx.y;
@@ -165,7 +185,7 @@ sep_gradient_kernel(const SepGradArgs A)
             double v = 0.0;
 #pragma unroll
             for (int w = 0; w < SEP_WARPS; ++w) v += red_sm[w][lane];
-            A.partial[(size_t)blockIdx.x * 7 + lane] = v;
+            A.partial[(size_t)item * 7 + lane] = v;
         }
     }
 }
@@ -267,7 +287,7 @@ int tomo_forward_separable_launch(const TomoGeom* g, const void* views, int n_pr
     A.nchunk = (A.nzp - 1 + SEP_OUT - 1) / SEP_OUT;
     // the last chunk must be able to serve floor planes up to nzp - 2 from SEP_CHUNK staged planes
     while ((A.nchunk - 1) * SEP_OUT + SEP_CHUNK < A.nzp) ++A.nchunk;
-    const double nblocks = (double)A.nxt * A.nchunk * n_proj;
+    const double nblocks = sep_grid_blocks(A.nxt, A.nchunk, n_proj);
     if (nblocks >= 2147483647.0) { tomo_set_error("separable forward: too many blocks for one launch"); return TOMO_E_RANGE; }
     sep_forward_kernel<<<(unsigned)nblocks, dim3(32, SEP_WARPS), 0, (cudaStream_t)stream>>>(A);
     return tomo_check_cuda(cudaGetLastError(), "sep_forward_kernel");
@@ -318,7 +338,7 @@ int tomo_grad_separable_launch(const TomoGeom* g, const void* views, int n_proj,
     A.syp = A.nzp;
     A.sxp = (g->ny + 2 * TOMO_PAD) * A.syp;
     tomo_grad_separable_tiles(g, &A.nxt, &A.nchunk);
-    const double nblocks = (double)A.nxt * A.nchunk * n_proj;
+    const double nblocks = sep_grid_blocks(A.nxt, A.nchunk, n_proj);
     if (nblocks >= 2147483647.0) { tomo_set_error("separable gradient: too many blocks for one launch"); return TOMO_E_RANGE; }
     sep_gradient_kernel<<<(unsigned)nblocks, dim3(32, SEP_WARPS), 0, (cudaStream_t)stream>>>(A);
     return tomo_check_cuda(cudaGetLastError(), "sep_gradient_kernel");
