@@ -117,7 +117,7 @@ __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
 
 // Measured on B200 (profiles/README.md): the forward march is fastest at 48 registers (5 blocks/SM) with the
 // sample loop unrolled twice; the gradient march is insensitive to both and keeps ptxas' own budget.
-__global__ void __launch_bounds__(TILE_Z * TILE_X, 5) ray_kernel_forward(const RayArgs A) { ray_kernel_body<false>(A); }
+__global__ void __launch_bounds__(TILE_Z * TILE_X, 40 / TILE_X) ray_kernel_forward(const RayArgs A) { ray_kernel_body<false>(A); }
 __global__ void __launch_bounds__(TILE_Z * TILE_X) ray_kernel_gradient(const RayArgs A) { ray_kernel_body<true>(A); }
 
 // Second pass of the deterministic reduction: one thread per (view, component) sums the block
