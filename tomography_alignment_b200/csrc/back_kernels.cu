@@ -402,6 +402,24 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     const int ty = bb % nty;
     const int tx = bb / nty;
     const int org[3] = {tx * TX - 1, ty * TY - 1, tz * TZ - 1};   // voxel coordinate of smem cell 0 (the low ghost cell)
+    // Nothing to scatter (every view of this table is left to the separable or the gather kernel): initialise the tile and leave,
+    // instead of walking the view table in every block
+    {
+        int need = 0;
+        for (int v = threadIdx.x; v < A.n_proj; v += TNW * 32) {
+            const double* __restrict__ V = A.views + (size_t)v * TOMO_VIEW_STRIDE;
+            need |= (V[V_NCOL] != 0.0) && !(A.skip_separable && V[V_SEP] != 0.0);
+        }
+        if (!__syncthreads_or(need)) {
+            if (!A.accumulate)
+                for (int i = threadIdx.x; i < TX * TY * 32; i += TNW * 32) {
+                    const int zz = i & 31, yy = (i >> 5) % TY, xx = (i >> 5) / TY;
+                    const int x = tx * TX + xx, y = ty * TY + yy, z = tz * TZ + zz;
+                    if (zz < TZ && x < A.nx && y < A.ny && z < A.nz) A.vol[((size_t)x * A.ny + y) * A.nz + z] = 0.f;
+                }
+            return;
+        }
+    }
     for (int i = threadIdx.x; i < TSMEM_FLOATS; i += TNW * 32) smem_raw[i] = 0.f;
     __syncthreads();
 
