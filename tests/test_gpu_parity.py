@@ -169,6 +169,26 @@ def test_voxel_backprojector_tma_equals_plain_kernel_at_256():
     assert float(v_plain.abs().max()) > 0
 
 
+@pytest.mark.parametrize("tilt", [0.02, 0.0])
+def test_banded_launch_order_with_a_ragged_last_band(tilt):
+    """200 detector columns = 25 x-tiles = two bands of 13 (the last one ragged): forward, gradient and both adjoints of the
+    generic (tilt != 0) and separable (tilt == 0) kernels against the oracle."""
+    shape, dshape, n_proj = (200, 120, 36), (200, 36), 3        # ny >= nx / 1.7: see DESIGN "known non-parity 2"
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, tilt=tilt, shift=1.5, phis=[0.2, 1.3, 2.6], seed=9)
+    rng = np.random.default_rng(2)
+    vol = rng.random(shape).astype(np.float32)
+    y = rng.random((n_proj,) + dshape).astype(np.float32)
+    assert rel_l2(be.forward(torch.as_tensor(vol)).cpu().numpy(), op.forward(vol)) <= TOL_PROJ
+    assert rel_l2(be.adjoint(torch.as_tensor(y)).cpu().numpy(), op.adjoint(y)) <= TOL_PROJ
+    out = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(y), want_proj=True, want_dproj=True)
+    for i in range(n_proj):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["proj"][i].cpu().numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][i].cpu().numpy(), gr) <= TOL_GRAD
+        res = y[i].ravel().astype(np.float64) - p
+        assert rel_l2(out["grad6"][i].cpu().numpy(), -gr @ res) <= TOL_GRAD
+
+
 def test_reference_numpy_golden_fixtures():
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_numpy_cases.npz"))
     for name in gold["case_names"]:
