@@ -16,9 +16,15 @@
  *   volume        float32 [nx][ny][nz], z fastest              src/ray_wt_grad.f90:38
  *   projections   float32 [n_proj][ndx][ndz], iz fastest       utilities/geometry.py:90-94,
  *                                                              utilities/projection_operators.py:108
- *   poses         float64 [n_proj][9] = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z
+ *   poses         float64 [n_proj][TOMO_POSE_STRIDE = 12] = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z,
+ *                 n_samples, r_length0, reserved
  *                 (angles, xyz_shift and Geometry.cor_shift rows of projection_operators.py:50-52,97-102;
- *                 only cor_x is used, ray_voxel_utilities.py:72-73)
+ *                 only cor_x is used, ray_voxel_utilities.py:72-73).  n_samples / r_length0 are the
+ *                 reference's n = int(r_length[0] / step_size) and r_length[0] (ray_voxel_utilities.py:85-88)
+ *                 as ITS numpy expression evaluates them: the quotient sits on an integer, so the count
+ *                 depends on last-bit rounding that only the caller's numpy can reproduce.  n_samples <= 0
+ *                 asks the library to evaluate the formula itself in float64 (may differ by one trailing
+ *                 sample, which lies sy - step beyond the rotation centre).
  *   gradients     order [tx, ty, tz, phi, alpha, beta]         utilities/ray_voxel_utilities.py:39-46
  */
 #ifndef TOMO_B200_H
@@ -46,7 +52,7 @@ extern "C" {
 
 /* Doubles per view in the device-side view table written by tomo_views_*. */
 #define TOMO_VIEW_STRIDE  160
-#define TOMO_POSE_STRIDE  9
+#define TOMO_POSE_STRIDE  12
 /* Zero border (voxels) of the padded volume on every side of every axis. */
 #define TOMO_PAD          2
 

@@ -13,6 +13,7 @@ import torch
 
 from oracle import oracle as O
 from tomography_alignment_b200 import Geometry, pose_table
+from tomography_alignment_b200.projection_operators import full_pose_table
 from tomography_alignment_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -116,7 +117,8 @@ class EmuBackend(_HostBackendBase):
     def set_poses(self, poses):
         super().set_poses(poses)
         self.views = np.zeros((self.n_proj, _lib.VIEW_STRIDE))
-        rc = self.L.tomo_views_compute_host(ctypes.byref(self.cg), _P(self.poses), self.n_proj, _P(self.views))
+        full = full_pose_table(self.geometry, self.poses)
+        rc = self.L.tomo_views_compute_host(ctypes.byref(self.cg), _P(full), self.n_proj, _P(self.views))
         _lib.check(rc, "tomo_views_compute_host")
 
     def _pad(self, vol):

@@ -7,6 +7,7 @@ import pytest
 
 from oracle import oracle as O
 from tomography_alignment_b200 import _lib, pose_table
+from tomography_alignment_b200.projection_operators import full_pose_table, reference_sample_counts
 from helpers import make_geoms, random_poses, _P
 
 V = dict(P00=0, U=3, W=6, D=9, N=12, RLEN=13, INVD=14, M=17, E=26, F=35, H=44, K=53, LINV=62, RB=71, VROT=74, VTR=83)
@@ -14,6 +15,7 @@ V = dict(P00=0, U=3, W=6, D=9, N=12, RLEN=13, INVD=14, M=17, E=26, F=35, H=44, K
 
 def views_for(g, poses):
     L = _lib.load()
+    poses = full_pose_table(g, poses)            # appends the reference's sample count (numpy-evaluated)
     out = np.zeros((poses.shape[0], _lib.VIEW_STRIDE))
     cg = g.to_c()
     _lib.check(L.tomo_views_compute_host(ctypes.byref(cg), _P(poses), poses.shape[0], _P(out)), "views")
@@ -35,8 +37,8 @@ def test_lattice_and_derivative_tables(shape, dshape, cor, step):
         p0 = v[V["P00"]:V["P00"] + 3, None] + v[V["U"]:V["U"] + 3, None] * ix + v[V["W"]:V["W"] + 3, None] * iz
         np.testing.assert_allclose(p0, vs.p0, rtol=0, atol=1e-12)
         np.testing.assert_allclose(v[V["D"]:V["D"] + 3, None] * np.ones_like(ix), vs.r_hat * vs.step_size, rtol=0, atol=1e-14)
-        assert int(v[V["N"]]) in (vs.n, vs.n + 1, vs.n - 1)       # int(r_length/step) sits on a rounding edge
-        assert abs(v[V["RLEN"]] - vs.r_length0) < 1e-12
+        assert int(v[V["N"]]) == vs.n                             # int(r_length/step) sits on a rounding edge: passed in
+        assert v[V["RLEN"]] == vs.r_length0
         der = vs.der()                                            # (9, 3, n_rays)
         for k in range(3):
             np.testing.assert_allclose(v[V["M"] + 3 * k:V["M"] + 3 * k + 3, None] * np.ones_like(ix), der[k], atol=1e-14)
@@ -56,7 +58,7 @@ def test_argument_errors_do_not_touch_cuda():
     L = _lib.load()
     g, _ = make_geoms((4, 4, 4), (4, 4), 1)
     cg = g.to_c()
-    poses = np.zeros((1, 9))
+    poses = np.zeros((1, _lib.POSE_STRIDE))
     out = np.zeros((1, _lib.VIEW_STRIDE))
     assert L.tomo_views_compute_host(ctypes.byref(cg), None, 1, _P(out)) == -1
     assert L.tomo_views_compute_host(ctypes.byref(cg), _P(poses), 0, _P(out)) == -1
@@ -95,3 +97,34 @@ def test_kernel_selection_flags():
     g2, _ = make_geoms((32, 32, 32), (32, 32), 1, vox_pix=[2.5, 1.0, 1.0])
     v2 = views_for(g2, pose_table(np.array([[0.0, 0.0, 0.0]]), np.zeros((1, 3)), g2.cor_shift))
     assert v2[0, VBOK] == 0 and v2[0, NVBIG] == 1
+
+
+@pytest.mark.parametrize("shape,dshape,step", [((16, 16, 16), (16, 16), 1.0), ((33, 9, 35), (33, 35), 1.0), ((5, 40, 3), (5, 3), 1.0),
+                                               ((24, 20, 18), (24, 18), 0.5), ((12, 12, 12), (18, 9), 1.7), ((7, 6, 5), (1, 1), 1.0),
+                                               ((64, 64, 64), (64, 64), 1.0)])
+def test_sample_count_is_the_reference_numpy_value(shape, dshape, step):
+    """n = int(r_length[0]/step_size) (ray_voxel_utilities.py:88) sits on an integer edge; the value handed to the C ABI must be the
+    one the reference's full-width numpy evaluation produces (oracle.ViewSetup restates those calls one for one), for every pose --
+    and when the caller leaves it out (n_samples = 0) the library's own float64 evaluation may differ by at most one."""
+    n_proj = 60
+    cor = np.zeros((n_proj, 3))
+    cor[:, 0] = np.random.default_rng(5).uniform(-1.5, 1.5, n_proj)
+    g, og = make_geoms(shape, dshape, n_proj, cor=cor, step=step)
+    phi, alpha, beta, xyz = random_poses(n_proj, 23, tilt=0.3, shift=3.0)
+    alpha[::3] = 0.0
+    beta[::4] = 0.0
+    phi[:4] = [0.0, np.pi / 2, np.pi, np.pi / 4]
+    poses = pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift)
+    cnt = reference_sample_counts(g, poses)
+    views = views_for(g, poses)
+    legacy = np.zeros((n_proj, _lib.POSE_STRIDE))
+    legacy[:, :9] = poses
+    views0 = views_for(g, legacy)
+    edge = 0
+    for i in range(n_proj):
+        vs = O.ViewSetup(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i])
+        assert int(cnt[i, 0]) == vs.n and cnt[i, 1] == vs.r_length0
+        assert int(views[i, V["N"]]) == vs.n
+        assert abs(int(views0[i, V["N"]]) - vs.n) <= 1
+        edge += int(views0[i, V["N"]]) != vs.n
+    print("views whose library-side count differs from numpy's:", edge, "of", n_proj)

@@ -12,7 +12,7 @@ from .geometry import TomoGeom
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TOMO_B200_LIB", os.path.join(_HERE, "libtomo_b200.so"))   # override: tuning builds only
 VIEW_STRIDE = 160
-POSE_STRIDE = 9
+POSE_STRIDE = 12
 PAD = 2
 
 _lib = None

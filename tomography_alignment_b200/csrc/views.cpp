@@ -80,11 +80,14 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
         const V3 r = sub(p1, p0);
         const double rlen = std::sqrt(r.v[0] * r.v[0] + r.v[1] * r.v[1] + r.v[2] * r.v[2]);   // :86
         const V3 rhat = {{r.v[0] / rlen, r.v[1] / rlen, r.v[2] / rlen}};
-        const int n = (int)(rlen / g->step_size);                  // :88 (truncation)
+        // :88 (truncation).  The quotient sits on an integer (r_length = 2 sy up to rounding), so the caller passes the
+        // count and length its own numpy evaluation produced (pose columns 9, 10); without them the formula is evaluated here.
+        const int n = (ps[9] > 0.0) ? (int)ps[9] : (int)(rlen / g->step_size);
+        const double rlen_ref = (ps[9] > 0.0 && ps[10] > 0.0) ? ps[10] : rlen;
         const V3 D = {{g->step_size * rhat.v[0], g->step_size * rhat.v[1], g->step_size * rhat.v[2]}};
 
         put(o + V_P00, p0); put(o + V_U, U); put(o + V_W, W); put(o + V_D, D);
-        o[V_N] = (double)n; o[V_RLEN] = rlen;
+        o[V_N] = (double)n; o[V_RLEN] = rlen_ref;
         for (int a = 0; a < 3; ++a) o[V_INVD + a] = (D.v[a] != 0.0) ? 1.0 / D.v[a] : 0.0;
 
         // translations: der[k] = (Rz Rx)[:, k]                    (:37-40)
@@ -107,7 +110,7 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
         // step-dependent parts on the untransformed ray vector d - s of ray 0   (:46-48), scaled by
         // d step / d j = step_size / r_length                                    (:148-151)
         const V3 rv = sub(d00, s00);
-        const double sc = g->step_size / rlen;
+        const double sc = g->step_size / rlen_ref;
         const V3 k3 = mul(dRp, mul(Rab, rv));
         const V3 k4 = mul(Rp, mul(dRa, mul(Rb, rv)));
         const V3 k5 = mul(Rpa, mul(dRb, rv));

@@ -106,8 +106,10 @@ class CudaBackend(object):
 
     # -- poses ---------------------------------------------------------------------------------
     def set_poses(self, poses):
-        """poses: float64 (n_proj, 9) = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z."""
-        poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, _lib.POSE_STRIDE))
+        """poses: float64 (n_proj, 9) = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z (``pose_table``); the
+        reference's per-view sample count is appended here (``full_pose_table``)."""
+        from .projection_operators import full_pose_table
+        poses = full_pose_table(self.geometry, poses)
         n = poses.shape[0]
         if self.views is None or self.views.shape[0] != n:
             self.views = torch.empty((n, _lib.VIEW_STRIDE), dtype=torch.float64, device=self.device)

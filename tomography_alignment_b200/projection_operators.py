@@ -62,6 +62,61 @@ def pose_table(angles, xyz_shift, cor_shift):
     return poses
 
 
+def _rot_z(a):
+    return np.array([(np.cos(a), -np.sin(a), 0.), (np.sin(a), np.cos(a), 0.), (0., 0., 1.)])
+
+
+def _rot_x(a):
+    return np.array([(1., 0., 0.), (0., np.cos(a), -np.sin(a)), (0., np.sin(a), np.cos(a))])
+
+
+def _rot_y(a):
+    return np.array([(np.cos(a), 0., np.sin(a)), (0., 1., 0.), (-np.sin(a), 0., np.cos(a))])
+
+
+def reference_sample_counts(geometry, poses):
+    """Per view: (n, r_length[0]) with n = int(r_length[0] / step_size), the number of samples the reference
+    marches along every ray (utilities/ray_voxel_utilities.py:85-88).
+
+    In exact arithmetic r_length[0] = 2*sy, so for the usual step sizes r_length[0]/step_size sits ON an
+    integer and int() returns 2*sy/step or one less depending on the last-bit rounding of the numpy
+    expression.  To march exactly the samples the reference marches, the expression is evaluated here with
+    the reference's own numpy calls (rotations.py:9-48, transform_points :6-12, forward_sparse :72-88) on the
+    first columns of the source / detector grids -- np.dot on (3,3)x(3,K) gives column 0 the same bits for
+    every K >= 2 (tests/test_views_host.py checks this against the full-width evaluation) -- and handed to
+    the C ABI in the pose record instead of being recomputed in C++."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, poses.shape[-1])
+    k = min(int(geometry.n_det), 4)
+    org = np.asarray(geometry.vox_origin, dtype=np.float64)[:, np.newaxis]
+    out = np.zeros((poses.shape[0], 2))
+    for i, ps in enumerate(poses):
+        phi, alpha, beta, t, cor_x = ps[0], ps[1], ps[2], ps[3:6], ps[6]
+        src = np.array(geometry.source_centers[:, :k], dtype=np.float64)
+        det = np.array(geometry.det_centers[:, :k], dtype=np.float64)
+        src[0, :] += cor_x
+        det[0, :] += cor_x
+        rot_pa = np.dot(_rot_z(phi), _rot_x(alpha))
+        p0 = np.dot(rot_pa, np.dot(_rot_y(beta), src) + t[:, np.newaxis]) - org
+        p1 = np.dot(rot_pa, np.dot(_rot_y(beta), det) + t[:, np.newaxis]) - org
+        r_length = np.linalg.norm(p1 - p0, axis=0)
+        out[i, 0] = int(r_length[0] / geometry.step_size)
+        out[i, 1] = r_length[0]
+    return out
+
+
+def full_pose_table(geometry, poses):
+    """(n_proj, 9) rows of ``pose_table`` -> the (n_proj, TOMO_POSE_STRIDE = 12) records of the C ABI:
+    columns 9, 10 = the reference's sample count and r_length[0] (``reference_sample_counts``), 11 reserved."""
+    poses = np.asarray(poses, dtype=np.float64)
+    poses = poses.reshape(-1, poses.shape[-1] if poses.ndim > 1 else 9)
+    if poses.shape[1] == 12:
+        return np.ascontiguousarray(poses)
+    full = np.zeros((poses.shape[0], 12), dtype=np.float64)
+    full[:, :9] = poses[:, :9]
+    full[:, 9:11] = reference_sample_counts(geometry, poses)
+    return full
+
+
 def _is_torch(x):
     return torch is not None and isinstance(x, torch.Tensor)
 
