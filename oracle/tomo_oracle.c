@@ -198,6 +198,161 @@ void orc_interp_grad_view(const double *p0, const double *rhat, long n_rays, lon
     }
 }
 
+/* ---- large-volume variants (tests at the BASELINE.json sizes) ----------------------------------
+ * Same loops as above with the volume / projections read as float32 (a float64 copy of a 1024^3
+ * volume is 8 GiB) and the work restricted to a caller-chosen subset, so that the oracle finishes
+ * in seconds at 512^3 / 1024^3.  Arithmetic is unchanged: float64 positions, weights, accumulators. */
+
+/* Rows rays[0..n_sel) of A applied to vol (orc_forward_view for a subset of rays). */
+void orc_forward_rays_f32(const double *p0, const double *rhat, long n_rays, long n, double step_size,
+                          long nx, long ny, long nz, const float *vol, const int64_t *rays, long n_sel,
+                          double *proj_sel)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long q = 0; q < n_sel; ++q) {
+        const long r = (long)rays[q];
+        double acc = 0.0;
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            for (int a = 0; a < 2; ++a) { if (!IN(X[a], nx)) continue;
+                for (int b = 0; b < 2; ++b) { if (!IN(Y[b], ny)) continue;
+                    for (int c = 0; c < 2; ++c) { if (!IN(Z[c], nz)) continue;
+                        acc += (WX[a] * WY[b] * WZ[c]) * (double)vol[(X[a] * ny + Y[b]) * nz + Z[c]];
+                    } } }
+        }
+        proj_sel[q] = acc;
+    }
+}
+
+/* orc_interp_grad_view for a subset of rays; det_img_sel (n_sel), grad_sel (6, n_sel) C-order. */
+void orc_interp_grad_rays_f32(const double *p0, const double *rhat, long n_rays, long n,
+                              double step_size, double r_length0, long nx, long ny, long nz,
+                              const float *vol, const double *der, const int64_t *rays, long n_sel,
+                              double *det_img_sel, double *grad_sel)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long q = 0; q < n_sel; ++q) {
+        const long r = (long)rays[q];
+        double acc = 0.0, ga[6] = {0, 0, 0, 0, 0, 0};
+        double d[9][3];
+        for (int k = 0; k < 9; ++k) for (int a = 0; a < 3; ++a)
+            d[k][a] = der[((long)k * 3 + a) * n_rays + r];
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const double st = (double)j * step_size / r_length0;
+            double g[6][3];
+            for (int a = 0; a < 3; ++a) {
+                g[0][a] = d[0][a]; g[1][a] = d[1][a]; g[2][a] = d[2][a];
+                g[3][a] = d[3][a] + st * d[6][a];
+                g[4][a] = d[4][a] + st * d[7][a];
+                g[5][a] = d[5][a] + st * d[8][a];
+            }
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            const double SG[2] = {-1.0, 1.0};
+            for (int a = 0; a < 2; ++a) { if (!IN(X[a], nx)) continue;
+                for (int b = 0; b < 2; ++b) { if (!IN(Y[b], ny)) continue;
+                    for (int c = 0; c < 2; ++c) { if (!IN(Z[c], nz)) continue;
+                        const double v = (double)vol[(X[a] * ny + Y[b]) * nz + Z[c]];
+                        acc += v * (WX[a] * WY[b] * WZ[c]);
+                        const double c1 = SG[a] * WY[b] * WZ[c] * v;
+                        const double c2 = SG[b] * WX[a] * WZ[c] * v;
+                        const double c3 = SG[c] * WX[a] * WY[b] * v;
+                        for (int k = 0; k < 6; ++k)
+                            ga[k] += c1 * g[k][0] + c2 * g[k][1] + c3 * g[k][2];
+                    } } }
+        }
+        det_img_sel[q] = acc;
+        for (int k = 0; k < 6; ++k) grad_sel[(long)k * n_sel + q] = ga[k];
+    }
+}
+
+/* orc_adjoint_view with the rays spread over the OpenMP threads (float64 atomic adds: the order of
+ * the float64 sums varies at the 1e-16 level, nothing else does) and float32 projections. */
+void orc_adjoint_view_par_f32(const double *p0, const double *rhat, long n_rays, long n, double step_size,
+                              long nx, long ny, long nz, const float *y, double *vol)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < n_rays; ++r) {
+        const double yr = (double)y[r];
+        if (yr == 0.0) continue;
+        for (long j = 0; j < n; ++j) {
+            sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+            const long X[2] = {s.fx, s.fx + 1}, Y[2] = {s.fy, s.fy + 1}, Z[2] = {s.fz, s.fz + 1};
+            const double WX[2] = {s.wfx, s.wcx}, WY[2] = {s.wfy, s.wcy}, WZ[2] = {s.wfz, s.wcz};
+            for (int a = 0; a < 2; ++a) { if (!IN(X[a], nx)) continue;
+                for (int b = 0; b < 2; ++b) { if (!IN(Y[b], ny)) continue;
+                    for (int c = 0; c < 2; ++c) { if (!IN(Z[c], nz)) continue;
+                        const double t = (WX[a] * WY[b] * WZ[c]) * yr;
+#pragma omp atomic
+                        vol[(X[a] * ny + Y[b]) * nz + Z[c]] += t;
+                    } } }
+        }
+    }
+}
+
+/* Entries voxels[0..n_sel) of A^T y for one view, WITHOUT scattering the whole view: the samples that can
+ * touch voxel v lie within one lattice step of the real-valued lattice coordinates (ix, iz, j) of v, where the
+ * lattice p(ix, iz, j) = p0[:, ix*ndz + iz] + j*step*rhat is the one orc_adjoint_view walks.  Every candidate
+ * sample in a window (the lattice-coordinate extent of a 2-voxel cube, plus 2) around the rounded coordinates is re-evaluated with make_sample (the same arithmetic
+ * as the scatter) and contributes iff v is one of its eight corners -- so the terms summed are exactly those the
+ * scatter adds to v.  tests/test_oracle_identities.py checks it against orc_adjoint_view entry for entry.
+ * out_sel[q] += contribution (accumulates over views). */
+void orc_adjoint_voxels_f32(const double *p0, const double *rhat, long ndx, long ndz, long n, double step_size,
+                            long nx, long ny, long nz, const float *y, const int64_t *voxels, long n_sel,
+                            double *out_sel)
+{
+    const long n_rays = ndx * ndz;
+    (void)nx;
+    /* lattice basis from the tabulated ray origins (affine in ix, iz) and ray 0's direction */
+    double B[3][3], O0[3];
+    for (int a = 0; a < 3; ++a) {
+        O0[a] = p0[a * n_rays];
+        B[a][0] = (ndx > 1) ? p0[a * n_rays + ndz] - O0[a] : (a == 0 ? 1.0 : 0.0);
+        B[a][1] = (ndz > 1) ? p0[a * n_rays + 1] - O0[a] : (a == 2 ? 1.0 : 0.0);
+        B[a][2] = step_size * rhat[a * n_rays];
+    }
+    const double det = B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1])
+                     - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0])
+                     + B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0]);
+    double Bi[3][3];
+    Bi[0][0] =  (B[1][1] * B[2][2] - B[1][2] * B[2][1]) / det;
+    Bi[0][1] = -(B[0][1] * B[2][2] - B[0][2] * B[2][1]) / det;
+    Bi[0][2] =  (B[0][1] * B[1][2] - B[0][2] * B[1][1]) / det;
+    Bi[1][0] = -(B[1][0] * B[2][2] - B[1][2] * B[2][0]) / det;
+    Bi[1][1] =  (B[0][0] * B[2][2] - B[0][2] * B[2][0]) / det;
+    Bi[1][2] = -(B[0][0] * B[1][2] - B[0][2] * B[1][0]) / det;
+    Bi[2][0] =  (B[1][0] * B[2][1] - B[1][1] * B[2][0]) / det;
+    Bi[2][1] = -(B[0][0] * B[2][1] - B[0][1] * B[2][0]) / det;
+    Bi[2][2] =  (B[0][0] * B[1][1] - B[0][1] * B[1][0]) / det;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long q = 0; q < n_sel; ++q) {
+        const long v = (long)voxels[q];
+        const long vz = v % nz, vy = (v / nz) % ny, vx = v / (nz * ny);
+        const double d[3] = {(double)vx - O0[0], (double)vy - O0[1], (double)vz - O0[2]};
+        long c[3], w[3];
+        for (int k = 0; k < 3; ++k) {
+            c[k] = (long)floor(Bi[k][0] * d[0] + Bi[k][1] * d[1] + Bi[k][2] * d[2] + 0.5);
+            /* |p - v| < 1 per axis maps to at most sum_a |Bi[k][a]| lattice steps along k; + rounding + margin */
+            w[k] = (long)ceil(fabs(Bi[k][0]) + fabs(Bi[k][1]) + fabs(Bi[k][2])) + 2;
+        }
+        double acc = 0.0;
+        for (long ix = c[0] - w[0]; ix <= c[0] + w[0]; ++ix) { if (!IN(ix, ndx)) continue;
+            for (long iz = c[1] - w[1]; iz <= c[1] + w[1]; ++iz) { if (!IN(iz, ndz)) continue;
+                const long r = ix * ndz + iz;
+                const double yr = (double)y[r];
+                for (long j = c[2] - w[2]; j <= c[2] + w[2]; ++j) { if (!IN(j, n)) continue;
+                    sample_t s; make_sample(p0, rhat, n_rays, r, j, step_size, &s);
+                    const long dx = vx - s.fx, dy = vy - s.fy, dz = vz - s.fz;
+                    if (dx < 0 || dx > 1 || dy < 0 || dy > 1 || dz < 0 || dz > 1) continue;
+                    acc += ((dx ? s.wcx : s.wfx) * (dy ? s.wcy : s.wfy) * (dz ? s.wcz : s.wfz)) * yr;
+                } } }
+        out_sel[q] += acc;
+    }
+}
+
 /* ---- orphan (matrix-free, never called from Python) voxel-driven semantics ----------------- */
 
 /* vox += bilinear gather of one view's detector image at the rotated voxel centres.

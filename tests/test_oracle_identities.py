@@ -91,3 +91,33 @@ def test_shard_views_is_array_split():
         assert np.array_equal(np.concatenate(parts), np.arange(n))
         sizes = [len(p) for p in parts]
         assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+@pytest.mark.parametrize("shape,dshape,kw", [((14, 12, 13), (14, 13), dict()), ((12, 12, 12), (16, 10), dict(tilt=0.25, shift=4.0)),
+                                             ((10, 16, 9), (10, 9), dict(step=0.5, cor=[0.4, 0, 0])),
+                                             ((10, 10, 10), (10, 10), dict(step=1.7)), ((9, 9, 9), (9, 9), dict(tilt=0.0, shift=0.0))])
+def test_subset_variants_match_the_full_loops(shape, dshape, kw):
+    """The ray / voxel subset entry points used by the 256^3 - 1024^3 GPU parity tests are the same loops as the full-view
+    oracle: rows of A x, rows of the gradient image, and entries of A^T y (the latter collected voxel by voxel from the
+    candidate samples around it -- must equal the scatter entry for entry, including border voxels and rays that miss)."""
+    n_proj = 4
+    pk = {k: kw[k] for k in ("tilt", "shift") if k in kw}
+    g, og = make_geoms(shape, dshape, n_proj, cor=kw.get("cor"), step=kw.get("step", 1.0))
+    phi, alpha, beta, xyz = random_poses(n_proj, 4, **pk)
+    op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    rng = np.random.default_rng(8)
+    vol = rng.random(shape).astype(np.float32)
+    y = rng.random((n_proj, og.n_det)).astype(np.float32)
+    rays = rng.choice(og.n_det, size=min(60, og.n_det), replace=False)
+    full = op.forward(vol.astype(np.float64))
+    for i in range(n_proj):
+        sub = O.forward_rays(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol, rays)
+        np.testing.assert_allclose(sub, full[i][rays], rtol=0, atol=1e-12)
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        ps, gs = O.forward_proj_grad_rays(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol, rays)
+        np.testing.assert_allclose(ps, p[rays], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(gs, gr[:, rays], rtol=0, atol=1e-10)
+    ref = op.adjoint(y.astype(np.float64))
+    np.testing.assert_allclose(O.adjoint_views_parallel(og, alpha, beta, phi, xyz, y), ref, rtol=0, atol=1e-11)
+    voxels = np.arange(og.n_vox)                       # every voxel: borders, corners, voxels no ray touches
+    np.testing.assert_allclose(O.adjoint_voxels(og, alpha, beta, phi, xyz, y, voxels), ref, rtol=0, atol=1e-11)
