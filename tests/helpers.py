@@ -64,8 +64,10 @@ class _HostBackendBase(object):
         return torch.as_tensor(np.ascontiguousarray(np.asarray(y, dtype=np.float32))).contiguous()
 
     def set_poses(self, poses):
-        self.poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 9))
+        poses = np.asarray(poses, dtype=np.float64)
+        self.poses = np.ascontiguousarray(poses.reshape(-1, poses.shape[-1])[:, :9])
         self.n_proj = self.poses.shape[0]
+        self._bound_state = None
 
 
 class OracleBackend(_HostBackendBase):

@@ -517,3 +517,58 @@ def test_error_codes_surface_as_exceptions():
         be.proj_grad(torch.zeros((8, 8, 8)), want_grad6=True)
     with pytest.raises(_lib.TomoError):
         _lib.check(be.lib.tomo_forward(be._g(), None, 2, None, None, None), "tomo_forward")
+
+
+@pytest.mark.parametrize("step,tilt", [(0.3, 0.05), (0.25, 0.12), (0.45, 0.02)])
+def test_tile_scatter_with_small_steps_and_tilt(step, tilt):
+    """step_size < 0.5 packs 1/step as many samples (and as much z drift per voxel) into a tile: the colour-class bound
+    (csrc/views.cpp) must still keep same-colour rays apart -- tile kernel against the oracle, against the independent gather
+    kernel, and bitwise repeatable."""
+    shape, dshape, n_proj = (64, 56, 66), (70, 70), 8
+    g, og, be, op, _ = setup(shape, dshape, n_proj, step=step, tilt=tilt, shift=2.0, seed=31)
+    y = np.random.default_rng(32).random((n_proj, og.n_det)).astype(np.float32)
+    ref = op.adjoint(y)
+    got = be.adjoint(torch.as_tensor(y))
+    assert rel_l2(got.cpu().numpy(), ref) <= TOL_PROJ
+    assert rel_l2(be.adjoint(torch.as_tensor(y), gather=True).cpu().numpy(), ref) <= TOL_PROJ
+    for _ in range(3):
+        assert torch.equal(be.adjoint(torch.as_tensor(y)), got)
+
+
+def test_out_buffers_are_validated():
+    g, og, be, op, _ = setup((16, 16, 16), (16, 16), 3)
+    vol = torch.rand((16, 16, 16), device="cuda")
+    y = torch.rand((3, 16, 16), device="cuda")
+    for bad in (torch.empty((3, 16, 15), device="cuda"), torch.empty((3, 16, 16)), torch.empty((3, 16, 16), device="cuda", dtype=torch.float64),
+                torch.empty((3, 16, 32), device="cuda")[:, :, ::2]):
+        with pytest.raises(ValueError):
+            be.forward(vol, out=bad)
+    for bad in (torch.empty((16, 16, 17), device="cuda"), torch.empty((16, 16, 16)), torch.empty((16, 32, 16), device="cuda")[:, ::2]):
+        with pytest.raises(ValueError):
+            be.adjoint(y, out=bad)
+        with pytest.raises(ValueError):
+            be.voxel_back(y, out=bad)
+    out_np = np.zeros((3, 16, 16), np.float32)            # numpy out_host is filled in place
+    r = be.forward_host(vol.cpu().numpy(), out_host=out_np)
+    assert r is out_np and np.array_equal(out_np, be.forward(vol).cpu().numpy())
+
+
+def test_operators_are_independent_on_the_gpu():
+    """Two operators from one ProjectionMatrix (true vs estimated poses) keep their own view tables."""
+    g, og = make_geoms((20, 20, 20), (20, 20), 4)
+    phi, alpha, beta, xyz = random_poses(4, 9)
+    pm = ProjectionMatrix(g, precision=np.float32, device="cuda:0")
+    A1 = pm.projection_matrix(alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    x = torch.rand(g.n_vox, device="cuda")
+    y1 = (A1 @ x).clone()
+    A2 = pm.projection_matrix(alpha=alpha, beta=beta, phi=phi + 0.3, xyz_shift=xyz)
+    A3 = pm.projection_matrix(phi=phi[:2])
+    r2 = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi + 0.3, xyz_shift=xyz)
+    for _ in range(2):
+        assert torch.equal(A1 @ x, y1) and (A1 @ x).numel() == 4 * g.n_det
+        assert rel_l2((A2 @ x).cpu().numpy(), r2.forward(x.cpu().numpy()).ravel()) <= TOL_PROJ
+        assert (A3 @ x).numel() == 2 * g.n_det
+        yy = torch.rand(4 * g.n_det, device="cuda")
+        assert rel_l2((A2.T @ yy).cpu().numpy(), r2.adjoint(yy.cpu().numpy().reshape(4, -1))) <= TOL_PROJ
+        pm.projection_gradient(x.reshape(20, 20, 20), alpha[0], beta[0], phi[0], xyz[0], g.cor_shift[0])
+    assert torch.equal(A1 @ x, y1)

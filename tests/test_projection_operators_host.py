@@ -151,3 +151,27 @@ def test_package_never_imports_the_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libtomo_oracle" not in src and "libtomo_emu" not in src, f
+
+
+def test_operators_from_one_projection_matrix_are_independent():
+    """The reference returns independent CSR matrices (projection_operators.py:54-76): a second projection_matrix() call,
+    a projection_gradient() call or a different view count must not re-pose an operator returned earlier."""
+    g, og, pm = make_pm(n_proj=4)
+    phi, alpha, beta, xyz = random_poses(4, 3)
+    x = np.random.default_rng(0).random(g.n_vox).astype(np.float32)
+    A1 = pm.projection_matrix(alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    r1 = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    y1 = A1.dot(x)
+    A2 = pm.projection_matrix(alpha=alpha, beta=beta, phi=phi + 0.3, xyz_shift=xyz)
+    r2 = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi + 0.3, xyz_shift=xyz)
+    A3 = pm.projection_matrix(phi=phi[:2], alpha=alpha[:2], beta=beta[:2], xyz_shift=xyz[:2])      # fewer views
+    assert A1.shape == (4 * g.n_det, g.n_vox) and A3.shape == (2 * g.n_det, g.n_vox)
+    for _ in range(2):                                 # interleaved applications
+        assert np.array_equal(A1.dot(x), y1) and A1.dot(x).shape == (4 * g.n_det,)
+        assert rel_l2(A2.dot(x), r2.forward(x).ravel()) < 1e-6
+        assert rel_l2(A3.dot(x), r1.forward(x)[:2].ravel()) < 1e-6
+        yy = np.random.default_rng(1).random(4 * g.n_det).astype(np.float32)
+        assert rel_l2(sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A1), yy), r1.adjoint(yy.reshape(4, -1))) < 1e-6
+        assert rel_l2(A2.T.dot(yy), r2.adjoint(yy.reshape(4, -1))) < 1e-6
+        pm.projection_gradient(x, alpha[0], beta[0], phi[0] + 1.0, xyz[0], g.cor_shift[0])    # re-poses the backend as well
+    assert np.array_equal(A1.dot(x), y1)

@@ -156,8 +156,11 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
             if (dxy > 1e-6 && wz >= 0.6) {
                 const double perp = std::fabs(U.v[0] * D.v[1] - U.v[1] * D.v[0]) / dxy;
                 const double wxy = std::sqrt(W.v[0] * W.v[0] + W.v[1] * W.v[1]);
-                const double span = 80.0;      // >= 2 * (tile x + tile y + 8) lattice steps for every tile size built
-                const double zdrift = span * (std::fabs(U.v[2]) + std::fabs(D.v[2]));
+                // lattice steps (in ix and in j) a tile can span: twice its xy extent plus ghost cells, per unit of xy advance
+                // of one step -- for step sizes below 1 a tile holds 1/step as many samples, each drifting D_z in z
+                const double uxy = std::sqrt(U.v[0] * U.v[0] + U.v[1] * U.v[1]);
+                const double ext = 2.0 * (TOMO_BT_X + TOMO_BT_Y + 8);
+                const double zdrift = ext * (std::fabs(U.v[2]) / std::fmax(uxy, 1e-6) + std::fabs(D.v[2]) / dxy);
                 const double n_over = std::ceil((2.0 + zdrift) / wz) - 1.0;
                 for (int C = 1; C <= 16; ++C)
                     if ((C * perp - n_over * wxy) / std::sqrt(2.0) >= 2.02) { ncol = C; break; }

@@ -37,6 +37,7 @@ class CudaBackend(object):
         self._volpad = None
         self._ws = None
         self.launches = 0        # kernels of ours launched so far (bench.py reports the count)
+        self._bound_state = None  # identity of the ProjectionOperator state whose poses are current
         self._copy = None        # side stream for host<->device copies overlapped with the kernels
         self._dbuf = {}          # cached device staging buffers of the host-buffer entry points
         self.h2d_bytes = 0       # bytes moved by the host-buffer entry points (bench.py reports them)
@@ -66,6 +67,15 @@ class CudaBackend(object):
         if y.numel() != self.n_proj * self.n_det:
             raise ValueError("projections have %d elements, operator expects %d" % (y.numel(), self.n_proj * self.n_det))
         return y
+
+    def _check_out(self, out, shape, what):
+        """``out=`` buffers are written by raw pointer: refuse anything the kernels cannot address."""
+        n = int(np.prod(shape))
+        if not isinstance(out, torch.Tensor) or out.device != self.device or out.dtype != torch.float32 \
+                or not out.is_contiguous() or out.numel() != n:
+            raise ValueError("%s: out= must be a contiguous float32 tensor of %d elements on %s"
+                             % (what, n, self.device))
+        return out
 
     def _views_at(self, first):
         """Device pointer of view record ``first`` (sub-tables are valid inputs of every operator)."""
@@ -111,13 +121,21 @@ class CudaBackend(object):
         from .projection_operators import full_pose_table
         poses = full_pose_table(self.geometry, poses)
         n = poses.shape[0]
-        if self.views is None or self.views.shape[0] != n:
-            self.views = torch.empty((n, _lib.VIEW_STRIDE), dtype=torch.float64, device=self.device)
+        # always a fresh table: operators returned by earlier projection_matrix() calls keep (and re-bind) theirs
+        self.views = torch.empty((n, _lib.VIEW_STRIDE), dtype=torch.float64, device=self.device)
+        self._bound_state = None
         with torch.cuda.device(self.device):
             rc = self.lib.tomo_views_upload(self._g(), poses.ctypes.data_as(ctypes.c_void_p), n, _ptr(self.views),
                                             self._stream())
         _lib.check(rc, "tomo_views_upload")
         self.n_proj = n
+
+    def bind_views(self, views, n_proj):
+        """Make a view table uploaded by an earlier set_poses() the current one again (ProjectionOperator._bind)."""
+        if views.device != self.device or views.dtype != torch.float64 or tuple(views.shape) != (n_proj, _lib.VIEW_STRIDE):
+            raise ValueError("bind_views: not a view table of this backend")
+        self.views = views
+        self.n_proj = int(n_proj)
 
     # -- operators -----------------------------------------------------------------------------
     def pad(self, vol):
@@ -137,6 +155,8 @@ class CudaBackend(object):
         volpad = self.pad(vol)
         if out is None:
             out = torch.empty((self.n_proj,) + self.det_shape, dtype=torch.float32, device=self.device)
+        else:
+            self._check_out(out, (self.n_proj,) + self.det_shape, "forward")
         with torch.cuda.device(self.device):
             rc = self.lib.tomo_forward(self._g(), _ptr(self.views), self.n_proj, _ptr(volpad), _ptr(out), self._stream())
         _lib.check(rc, "tomo_forward")
@@ -150,6 +170,8 @@ class CudaBackend(object):
         if out is None:
             out = torch.empty(self.vol_shape, dtype=torch.float32, device=self.device)
             accumulate = False
+        else:
+            self._check_out(out, self.vol_shape, "adjoint")
         with torch.cuda.device(self.device):
             if gather:
                 rc = self.lib.tomo_back_adjoint_gather(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out),
@@ -174,6 +196,12 @@ class CudaBackend(object):
                 raise ValueError("volume has %d elements, geometry expects %d" % (x_host.numel(), int(np.prod(self.vol_shape))))
         if out_host is None:
             out_host = torch.empty((self.n_proj,) + self.det_shape, dtype=torch.float32, pin_memory=True)
+        ret = out_host
+        out_host = torch.as_tensor(out_host)                 # numpy arrays are wrapped, not copied
+        if out_host.dtype != torch.float32 or not out_host.is_contiguous() or out_host.numel() != self.n_proj * self.n_det \
+                or out_host.device.type != "cpu":
+            raise ValueError("forward_host: out_host must be a contiguous float32 host buffer of %d elements"
+                             % (self.n_proj * self.n_det))
         out3 = out_host.reshape((self.n_proj,) + self.det_shape)
         cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
         if vol_dev is None:
@@ -197,12 +225,15 @@ class CudaBackend(object):
         cp.synchronize()
         cur.wait_stream(cp)
         self.d2h_bytes += 4 * out3.numel()
-        return out_host
+        return ret
 
     def adjoint_host(self, y_host, out_host=None, chunk_views=None, to_host=True):
         """vol = A^T y with HOST input and output: projection chunks go up on a side stream while the
         previous chunk is backprojected (accumulating launches), the volume comes down once.
-        ``to_host=False`` returns the device volume instead (callers that all-reduce before the download)."""
+        ``to_host=False`` returns the device volume instead (callers that all-reduce before the download): it is
+        this backend's reusable staging buffer, valid until the next ``*_host`` call on the backend -- clone it to
+        keep it.  Either way the call returns only after the uploads of ``y_host`` have completed, so the host
+        buffer may be reused at once."""
         y_host = self._host(y_host)
         if y_host.numel() != self.n_proj * self.n_det:
             raise ValueError("projections have %d elements, operator expects %d" % (y_host.numel(), self.n_proj * self.n_det))
@@ -231,6 +262,7 @@ class CudaBackend(object):
                 self.launches += 4
         self.h2d_bytes += 4 * y_host.numel()
         if not to_host:
+            cp.synchronize()                     # the pinned input may be reused by the caller from here on
             return vol_d
         out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
         cur.synchronize()
@@ -240,7 +272,8 @@ class CudaBackend(object):
     def proj_grad_host(self, vol_host, meas_host, chunk_views=None, vol_dev=None, to_host=True):
         """Fused residual gradients with HOST inputs: returns (grad6 (n_proj, 6), cost (n_proj,)) float64 CPU
         tensors (device tensors with ``to_host=False``).  The measured projections go up in chunks under the
-        previous chunk's kernel.  ``vol_dev``: the volume is already on this device."""
+        previous chunk's kernel.  ``vol_dev``: the volume is already on this device.  With ``to_host=False`` the
+        returned tensors are this backend's reusable buffers (valid until the next ``proj_grad_host`` call)."""
         meas_host = self._host(meas_host)
         if vol_dev is None:
             vol_host = self._host(vol_host).reshape(-1)
@@ -280,6 +313,9 @@ class CudaBackend(object):
                 self.launches += 2
         self.h2d_bytes += 4 * meas_host.numel()
         if not to_host:
+            cp.synchronize()                     # uploads of the pinned inputs are complete
+            if vol_dev is None:
+                cur.synchronize()                # ... including the volume, copied on the compute stream
             return grad6, cost
         g6, c = grad6.cpu(), cost.cpu()          # synchronises `cur`
         self.d2h_bytes += 8 * (g6.numel() + c.numel())
@@ -293,6 +329,8 @@ class CudaBackend(object):
         if out is None:
             out = torch.empty(self.vol_shape, dtype=torch.float32, device=self.device)
             accumulate = False
+        else:
+            self._check_out(out, self.vol_shape, "voxel_back")
         with torch.cuda.device(self.device):
             rc = self.lib.tomo_back_voxel_bilinear(self._g(), _ptr(self.views), self.n_proj, org, _ptr(y), _ptr(out),
                                                    int(bool(accumulate)), self._stream())

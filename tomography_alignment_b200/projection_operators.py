@@ -135,8 +135,13 @@ class ProjectionOperator(object):
     ndim = 2
 
     def __init__(self, backend, n_proj, n_det, n_vox, precision=np.float32, voxel_mask=None,
-                 transposed=False, all_masked=False):
+                 transposed=False, all_masked=False, poses=None, _state=None):
         self._backend = backend
+        # The operator owns its poses (like the reference's CSR matrix owns its entries): a later
+        # projection_matrix() call on the same ProjectionMatrix re-poses the shared backend, so every application
+        # first re-binds this operator's own view table (a device tensor kept in _state, shared with the transposes).
+        self._poses = None if poses is None else np.array(poses, dtype=np.float64, copy=True)
+        self._state = {"views": None} if _state is None else _state
         self._n_proj, self._n_det, self._n_vox = int(n_proj), int(n_det), int(n_vox)
         self._transposed = bool(transposed)
         self._precision = precision
@@ -157,7 +162,7 @@ class ProjectionOperator(object):
 
     def transpose(self, axes=None, copy=False):
         return ProjectionOperator(self._backend, self._n_proj, self._n_det, self._n_vox, self._precision,
-                                  self._mask, not self._transposed, self._all_masked)
+                                  self._mask, not self._transposed, self._all_masked, self._poses, self._state)
 
     @property
     def T(self):
@@ -176,6 +181,18 @@ class ProjectionOperator(object):
         return self.transpose().__matmul__(y)
 
     # -- application -----------------------------------------------------------------------------
+    def _bind(self):
+        """Make the backend apply THIS operator's poses (no-op while nobody else has re-posed it)."""
+        b = self._backend
+        if self._poses is None or getattr(b, "_bound_state", None) is self._state:
+            return
+        if self._state["views"] is not None and hasattr(b, "bind_views"):
+            b.bind_views(self._state["views"], self._n_proj)
+        else:
+            b.set_poses(self._poses)
+            self._state["views"] = getattr(b, "views", None)
+        b._bound_state = self._state
+
     def _mask_on(self, like):
         if self._mask_dev is None:
             self._mask_dev = torch.as_tensor(self._mask.astype(np.float32), device=like.device)
@@ -186,6 +203,7 @@ class ProjectionOperator(object):
             raise ValueError("dimension mismatch: operator has %d columns, vector has %d entries"
                              % (self._n_vox, _numel(x)))
         was_torch = _is_torch(x)
+        self._bind()
         if not (was_torch and x.is_cuda) and self._mask is None and hasattr(self._backend, "forward_host"):
             # host buffers: copies overlapped with the kernels in view chunks (cuda_backend.forward_host)
             y = self._backend.forward_host(x).reshape(-1)
@@ -204,6 +222,7 @@ class ProjectionOperator(object):
             raise ValueError("dimension mismatch: operator has %d rows, vector has %d entries"
                              % (self._n_proj * self._n_det, _numel(y)))
         was_torch = _is_torch(y)
+        self._bind()
         if not (was_torch and y.is_cuda) and self._mask is None and hasattr(self._backend, "adjoint_host"):
             v = self._backend.adjoint_host(y).reshape(-1)
             return v if was_torch else v.numpy().astype(np.result_type(self._precision, np.asarray(y).dtype), copy=False)
@@ -248,6 +267,8 @@ class ProjectionMatrix(object):
         poses = pose_table(self.angles, self.xyz_shift, cor[:self.n_proj])
         backend = self._get_backend()
         backend.set_poses(poses)
+        state = {"views": getattr(backend, "views", None)}
+        backend._bound_state = state
         mask, all_masked = None, False
         if voxel_mask is not None:
             mask = np.asarray(voxel_mask).ravel().astype(bool)
@@ -255,7 +276,7 @@ class ProjectionMatrix(object):
                 print('entire object is masked')     # projection_operators.py:63-65
                 all_masked = True
         return ProjectionOperator(backend, self.n_proj, self.geometry.n_det, self.geometry.n_vox,
-                                  self.precision, mask, False, all_masked)
+                                  self.precision, mask, False, all_masked, poses, state)
 
     def projection_gradient(self, rec, alpha, beta, phi, xyz_shift, cor_shift):
         """One view: (proj (n_det,), grad (6, n_det)), gradient rows [tx, ty, tz, phi, alpha, beta]
