@@ -14,6 +14,7 @@ if os.environ.get("UNTILTED"):
 sel = np.linspace(0, 719, n_proj).astype(int)
 be = CudaBackend(g, "cuda:0")
 be.set_poses(pose_table(np.array([phi, alpha, beta]).T[sel], xyz[sel], g.cor_shift))
+torch.manual_seed(0)
 vol = torch.rand((n, n, n), device="cuda")
 y = torch.rand((n_proj, n, n), device="cuda")
 bp = torch.empty((n, n, n), device="cuda")
@@ -27,7 +28,9 @@ def t(fn, reps=3):
     return s.elapsed_time(e) / reps
 out = {"lib": os.path.basename(os.environ.get("TOMO_B200_LIB", "default")), "n": n, "views": n_proj}
 if "f" in which: out["fwd_ms"] = t(lambda: be.forward(vol, out=proj))
-if "b" in which: out["back_ms"] = t(lambda: be.adjoint(y, out=bp))
+if "b" in which:
+    out["back_ms"] = t(lambda: be.adjoint(y, out=bp))
+    out["back_checksum"] = int(bp.view(torch.int32).to(torch.int64).sum().item())      # bitwise fingerprint for A/B builds
 if "v" in which: out["voxback_ms"] = t(lambda: be.voxel_back(y, out=bp))
 if "g" in which: out["grad_ms"] = t(lambda: be.proj_grad(vol, meas=y, want_proj=False, want_dproj=False, repad=False))
 print(json.dumps(out))

@@ -266,9 +266,10 @@ struct TileView {
     float Bc[3], U[3], W[3], D[3], invD[3];
     float df[3];            // fractional part of |D|
     int   di_step;          // integer part of |D| folded into the address step (mirrored frame)
-    int   zi_step;
     int   ix_lo, ix_hi, iz_lo, iz_hi, jc, djmin, djmax, ncol;
     float dupthr;           // same-z-cell test threshold for adjacent lanes
+    int   view;             // index of the view these constants belong to; -1: no view left for this tile
+    int   sgn;              // bit 2/1/0 set: D_x / D_y / D_z negative
 };
 
 // Four read-modify-writes s[off_k] += w_k * wz on shared memory as two packed fp32x2 FMAs; the four loads
@@ -304,9 +305,11 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
     const unsigned acc_b = (unsigned)__cvta_generic_to_shared(acc);
     unsigned dummy_b = acc_b - 4u * TGUARD + 4u * DUMMY;
     asm volatile("" : "+r"(dummy_b));                       // a register, not a per-sample recomputation
-    for (int c = 0; c < tv.ncol; ++c) {
-        const int first = tv.ix_lo + (((c - tv.ix_lo) % tv.ncol) + tv.ncol) % tv.ncol;
-        for (int ix = first + tv.ncol * warp; ix <= tv.ix_hi; ix += tv.ncol * TNW) {
+    const float df0 = tv.df[0], df1 = tv.df[1], df2 = tv.df[2], dupthr = tv.dupthr;
+    const int ncol = tv.ncol, ix_lo = tv.ix_lo, ix_hi = tv.ix_hi;
+    for (int c = 0; c < ncol; ++c) {
+        const int first = ix_lo + (((c - ix_lo) % ncol) + ncol) % ncol;
+        for (int ix = first + ncol * warp; ix <= ix_hi; ix += ncol * TNW) {
             for (int izb = tv.iz_lo; izb <= tv.iz_hi; izb += 32) {
                 const int iz = izb + lane;
                 const bool valid = iz <= tv.iz_hi;
@@ -349,7 +352,7 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                     const bool act = k < span;
                     // lane l+1 sits in lane l's z cell iff its own fraction says so (no shuffle needed):
                     // mirrored z decreases (SGZ < 0) or increases (SGZ > 0) by W_z per lane
-                    const bool dup = act && ((SGZ > 0) ? (f2 >= tv.dupthr) : (f2 < 1.f - tv.dupthr));
+                    const bool dup = act && ((SGZ > 0) ? (f2 >= dupthr) : (f2 < 1.f - dupthr));
                     // corner weights as the pairs (x0y0, x1y0) and (x0y1, x1y1) of the packed FMAs
                     const float wx1 = f0 * yv, wx0 = yv - wx1;
                     const float2 wx = make_float2(wx0, wx1);
@@ -377,7 +380,7 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                     }
                     // advance one sample: one-sided carries, the strides folded into one address increment
                     ++k;
-                    f0 += tv.df[0]; f1 += tv.df[1]; f2 += tv.df[2];
+                    f0 += df0; f1 += df1; f2 += df2;
                     int inc = stepoff;
                     if (f0 >= 1.0f) { f0 -= 1.0f; inc = stepx; }
                     if (f1 >= 1.0f) { f1 -= 1.0f; inc += STY; }
@@ -388,6 +391,60 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
         }
         __syncthreads();
     }
+}
+
+// Constants of the next view (from `view` on) that has rays crossing the tile, or tv.view = -1.  One thread, float64.
+__device__ __noinline__ void tile_next_view(const BackArgs& A, int view, const int org[3], TileView& tv)
+{
+    constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
+    // a sample is ours iff its floor cell lies in [0, T] per axis, i.e. 0 <= p_s < T+1 (smem coordinates)
+    const double hw[3] = {0.5 * (TX + 1), 0.5 * (TY + 1), 0.5 * (TZ + 1)};
+    for (; view < A.n_proj; ++view) {
+        const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+        tv.ncol = (int)V[V_NCOL];
+        if (tv.ncol == 0) continue;                      // outside the scatter envelope: the gather kernel adds it
+        if (A.skip_separable && V[V_SEP] != 0.0) continue;   // untilted view: the separable adjoint adds it
+        // lattice coordinates of the active box: centre +- sum |Linv| * half widths (exact for a linear map)
+        double B[3], cc[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            B[a] = V[V_P00 + a] - (double)org[a];        // p_s = B + ix U + iz W + j D
+            cc[a] = hw[a] - B[a];
+        }
+        double lc[3], lr[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lc[k] = V[V_LINV + 3 * k] * cc[0] + V[V_LINV + 3 * k + 1] * cc[1] + V[V_LINV + 3 * k + 2] * cc[2];
+            lr[k] = fabs(V[V_LINV + 3 * k]) * hw[0] + fabs(V[V_LINV + 3 * k + 1]) * hw[1] + fabs(V[V_LINV + 3 * k + 2]) * hw[2] + 1e-3;
+        }
+        tv.ix_lo = max(0, (int)ceil(fmax(lc[0] - lr[0], -1.0)));
+        tv.ix_hi = min(A.ndx - 1, (int)floor(fmin(lc[0] + lr[0], 2.0e9)));
+        tv.iz_lo = max(0, (int)ceil(fmax(lc[1] - lr[1], -1.0)));
+        tv.iz_hi = min(A.ndz - 1, (int)floor(fmin(lc[1] + lr[1], 2.0e9)));
+        const int nsamp = (int)V[V_N];
+        const int j_lo = max(0, (int)ceil(fmax(lc[2] - lr[2], -1.0))), j_hi = min(nsamp - 1, (int)floor(fmin(lc[2] + lr[2], 2.0e9)));
+        if (tv.ix_lo > tv.ix_hi || tv.iz_lo > tv.iz_hi || j_lo > j_hi) continue;   // nothing of this view crosses the tile
+        tv.jc = (j_lo + j_hi) / 2;
+        tv.djmin = j_lo - tv.jc;
+        tv.djmax = j_hi - tv.jc + 1;
+        tv.di_step = 0; tv.sgn = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double d = V[V_D + a], ad = fabs(d), ai = floor(ad);
+            tv.Bc[a] = (float)(B[a] + (double)tv.ix_lo * V[V_U + a] + (double)tv.iz_lo * V[V_W + a] + (double)tv.jc * d);
+            tv.U[a] = (float)V[V_U + a]; tv.W[a] = (float)V[V_W + a]; tv.D[a] = (float)d;
+            tv.invD[a] = (float)V[V_INVD + a];
+            tv.df[a] = (float)(ad - ai);
+            const int sg = (d < 0.0) ? -1 : 1;
+            if (sg < 0) tv.sgn |= 4 >> a;
+            tv.di_step += (int)ai * sg * ((a == 0) ? TSY * TSZ : (a == 1) ? TSZ : 1);
+        }
+        // adjacent lanes share a z cell iff frac >= W_z (mirrored: frac < 1 - W_z); margin for float32 marching
+        tv.dupthr = (float)fabs(V[V_W + 2]) - 2e-4f;
+        tv.view = view;
+        return;
+    }
+    tv.view = -1;
 }
 
 __global__ void __launch_bounds__(TNW * 32)
@@ -423,57 +480,19 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     for (int i = threadIdx.x; i < TSMEM_FLOATS; i += TNW * 32) smem_raw[i] = 0.f;
     __syncthreads();
 
+    // Per-view constants: computed once per (block, view) by one thread -- for the NEXT view, while the block marches the current
+    // one -- and handed over through shared memory (they used to be recomputed in float64 by every thread).
+    __shared__ TileView tvs[2];
+    if (threadIdx.x == 0) tile_next_view(A, 0, org, tvs[0]);
+    __syncthreads();
     const size_t n_det = (size_t)A.ndx * A.ndz;
-    // a sample is ours iff its floor cell lies in [0, T] per axis, i.e. 0 <= p_s < T+1 (smem coordinates)
-    const double hw[3] = {0.5 * (TX + 1), 0.5 * (TY + 1), 0.5 * (TZ + 1)};
-
-    for (int view = 0; view < A.n_proj; ++view) {
-        const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
-        TileView tv;
-        const double vsep = V[V_SEP];                    // both flags loaded before the first branch
-        tv.ncol = (int)V[V_NCOL];
-        if (tv.ncol == 0) continue;                      // outside the scatter envelope: the gather kernel adds it
-        if (A.skip_separable && vsep != 0.0) continue;   // untilted view: the separable adjoint adds it
-        // lattice coordinates of the active box: centre +- sum |Linv| * half widths (exact for a linear map)
-        double B[3], cc[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            B[a] = V[V_P00 + a] - (double)org[a];        // p_s = B + ix U + iz W + j D
-            cc[a] = hw[a] - B[a];
-        }
-        double lc[3], lr[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            lc[k] = V[V_LINV + 3 * k] * cc[0] + V[V_LINV + 3 * k + 1] * cc[1] + V[V_LINV + 3 * k + 2] * cc[2];
-            lr[k] = fabs(V[V_LINV + 3 * k]) * hw[0] + fabs(V[V_LINV + 3 * k + 1]) * hw[1] + fabs(V[V_LINV + 3 * k + 2]) * hw[2] + 1e-3;
-        }
-        tv.ix_lo = max(0, (int)ceil(fmax(lc[0] - lr[0], -1.0)));
-        tv.ix_hi = min(A.ndx - 1, (int)floor(fmin(lc[0] + lr[0], 2.0e9)));
-        tv.iz_lo = max(0, (int)ceil(fmax(lc[1] - lr[1], -1.0)));
-        tv.iz_hi = min(A.ndz - 1, (int)floor(fmin(lc[1] + lr[1], 2.0e9)));
-        const int nsamp = (int)V[V_N];
-        const int j_lo = max(0, (int)ceil(fmax(lc[2] - lr[2], -1.0))), j_hi = min(nsamp - 1, (int)floor(fmin(lc[2] + lr[2], 2.0e9)));
-        if (tv.ix_lo > tv.ix_hi || tv.iz_lo > tv.iz_hi || j_lo > j_hi) continue;   // block-uniform: nothing of this view crosses the tile
-        tv.jc = (j_lo + j_hi) / 2;
-        tv.djmin = j_lo - tv.jc;
-        tv.djmax = j_hi - tv.jc + 1;
-        int sx = 1, sy = 1, sz = 1;
-        tv.di_step = 0; tv.zi_step = 0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const double d = V[V_D + a], ad = fabs(d), ai = floor(ad);
-            tv.Bc[a] = (float)(B[a] + (double)tv.ix_lo * V[V_U + a] + (double)tv.iz_lo * V[V_W + a] + (double)tv.jc * d);
-            tv.U[a] = (float)V[V_U + a]; tv.W[a] = (float)V[V_W + a]; tv.D[a] = (float)d;
-            tv.invD[a] = (float)V[V_INVD + a];
-            tv.df[a] = (float)(ad - ai);
-            const int sg = (d < 0.0) ? -1 : 1;
-            if (a == 0) sx = sg; else if (a == 1) sy = sg; else sz = sg;
-            tv.di_step += (int)ai * sg * ((a == 0) ? TSY * TSZ : (a == 1) ? TSZ : 1);
-        }
-        // adjacent lanes share a z cell iff frac >= W_z (mirrored: frac < 1 - W_z); margin for float32 marching
-        tv.dupthr = (float)fabs(V[V_W + 2]) - 2e-4f;
-        const float* __restrict__ P = A.proj + (size_t)view * n_det;
-        switch ((sx < 0 ? 4 : 0) | (sy < 0 ? 2 : 0) | (sz < 0 ? 1 : 0)) {       // block-uniform
+    for (int buf = 0; ; buf ^= 1) {
+        const TileView& tv = tvs[buf];       // rewritten two views from now, after the barriers that end this view's classes
+        if (tv.view < 0) break;              // block-uniform
+        if (threadIdx.x == TNW * 32 - 1) tile_next_view(A, tv.view + 1, org, tvs[buf ^ 1]);
+        __syncwarp();
+        const float* __restrict__ P = A.proj + (size_t)tv.view * n_det;
+        switch (tv.sgn) {                                                       // block-uniform
             case 0: tile_march_view< 1,  1,  1>(acc, tv, P, A.ndz, lane, warp); break;
             case 1: tile_march_view< 1,  1, -1>(acc, tv, P, A.ndz, lane, warp); break;
             case 2: tile_march_view< 1, -1,  1>(acc, tv, P, A.ndz, lane, warp); break;
