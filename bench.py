@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--cpu-size", type=int, default=256, help="volume size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--slabs", type=int, default=8, help="x-slabs of the backprojection (all-reduce of slab k under the kernel of slab k+1)")
     ap.add_argument("--host-phantom", action="store_true",
                     help="build the phantom with numpy on the host (profiling runs: keeps torch's phantom kernels out of ncu launch lists)")
     return ap.parse_args()
@@ -185,7 +186,7 @@ def run_b200(a):
     from tomography_alignment_b200 import Geometry, ProjectionMatrix, pose_table
     from tomography_alignment_b200.cuda_backend import CudaBackend
     from tomography_alignment_b200.phantom import benchmark_poses, shepp3d
-    from tomography_alignment_b200.sharding import shard_views
+    from tomography_alignment_b200.sharding import SharedHostBuffer, adjoint_allreduce, shard_views
 
     log("torch imported")
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,15 +230,17 @@ def run_b200(a):
     def step():
         be.forward(vol, out=proj)                                   # pad + forward, all local views
         res = meas - proj                                            # residual (elementwise, torch)
-        be.adjoint(res, out=bp)                                      # exact adjoint, all local views
-        if world > 1:
-            dist.all_reduce(bp)
+        # exact adjoint of all local views in x-slabs; the NCCL all-reduce of a finished slab (recon/sirt_mpi.py:103) runs
+        # on NVLink while the next slab -- and, for the last slabs, the gradient kernel -- is computed
+        _, works = adjoint_allreduce(be, res, bp, None, a.slabs, reduce=world > 1)
         out = be.proj_grad(vol, meas=meas, want_proj=False, want_dproj=False, repad=False)
         if world > 1:
             table.zero_()
             table[idx, :6] = out["grad6"]
             table[idx, 6] = out["cost"]
             dist.all_reduce(table)
+        for w in works:                                              # the step ends with the summed volume complete
+            w.wait()
         return out
 
     def sync_all():
@@ -363,12 +366,31 @@ def run_b200(a):
 
         d_vol = torch.empty((n, n, n), dtype=torch.float32, device=dev)
         g_tab = torch.zeros((n_proj, 7), dtype=torch.float64, device=dev)
+        sharded_io = world > 1 and n % world == 0
+        if sharded_io:
+            # one box, one host memory: the volume, the backprojection and the projections live in host buffers every rank
+            # sees (POSIX shared memory, page-locked in each process); each rank moves only its 1/N over its own PCIe link
+            sh_vol = SharedHostBuffer("tomo_b200_bench_vol", (n, n, n))
+            sh_bp = SharedHostBuffer("tomo_b200_bench_bp", (n, n, n))
+            sh_proj = SharedHostBuffer("tomo_b200_bench_proj", (n_proj, n, n))
+            if rank == 0:
+                sh_vol.tensor.copy_(h_vol)
+            dist.barrier()
+            xs = n // world
+            my_x = slice(rank * xs, (rank + 1) * xs)
+            bp_slab = torch.empty((xs, n, n), dtype=torch.float32, device=dev)
+            log("shared host buffers ready (pinned: %s)" % (sh_vol.pinned and sh_bp.pinned and sh_proj.pinned))
 
         def upload_volume():
-            """The replicated volume: rank 0 uploads it from pinned host memory, the other ranks receive it over NVLink
-            (what the bcast of recon/regularized_mpi.py:137 does, on the device)."""
+            """The replicated volume, once per step: every rank uploads its x-slab from the shared host buffer and the slabs
+            are all-gathered over NVLink (rank 0 uploading everything and broadcasting when nx does not divide)."""
             if world == 1:
                 return None
+            if sharded_io:
+                d_vol[my_x].copy_(sh_vol.tensor[my_x], non_blocking=True)
+                be.h2d_bytes += 4 * xs * n * n
+                dist.all_gather_into_tensor(d_vol, d_vol[my_x])
+                return d_vol
             if rank == 0:
                 d_vol.copy_(h_vol, non_blocking=True)
                 be.h2d_bytes += 4 * h_vol.numel()
@@ -377,18 +399,24 @@ def run_b200(a):
 
         def e2e_step():
             # host buffers in, host buffers out; copies are issued inside the calls (view chunks, side stream)
-            be.forward_host(h_vol, out_host=h_proj, vol_dev=upload_volume())   # H2D volume, forward, D2H projections
             if world == 1:
+                be.forward_host(h_vol, out_host=h_proj)                         # H2D volume, forward, D2H projections
                 be.adjoint_host(h_meas, out_host=h_bp)                          # H2D projections, adjoint, D2H volume
-            else:                                                               # Allreduce of recon/sirt_mpi.py:103, then rank 0 downloads
-                v = be.adjoint_host(h_meas, out_host=None, to_host=False)
+                return be.proj_grad_host(None, h_meas, vol_dev=be._buf("vol", be.vol_shape))   # H2D measured, D2H (n, 6) gradients
+            dv = upload_volume()                                                # H2D volume: once per step, 1/N per rank
+            out_rows = sh_proj.tensor[mine[0]:mine[-1] + 1] if sharded_io else h_proj
+            be.forward_host(None, out_host=out_rows, vol_dev=dv)                # forward, D2H of this rank's views
+            v = be.adjoint_host(h_meas, out_host=None, to_host=False)           # H2D projections, adjoint (device volume)
+            if sharded_io:                                                      # reduce-scatter instead of the Allreduce of
+                dist.reduce_scatter_tensor(bp_slab, v)                          # recon/sirt_mpi.py:103: each rank downloads
+                sh_bp.tensor[my_x].copy_(bp_slab, non_blocking=True)            # its summed x-slab into the shared buffer
+                be.d2h_bytes += 4 * bp_slab.numel()
+            else:
                 dist.all_reduce(v)
                 if rank == 0:
                     h_bp.copy_(v)
                     be.d2h_bytes += 4 * v.numel()
-            if world == 1:
-                return be.proj_grad_host(h_vol, h_meas)                         # H2D volume + measured, D2H (n, 6) gradients
-            g6, c = be.proj_grad_host(None, h_meas, vol_dev=upload_volume(), to_host=False)
+            g6, c = be.proj_grad_host(None, h_meas, vol_dev=dv, to_host=False)
             g_tab.zero_()
             g_tab[idx, :6] = g6
             g_tab[idx, 6] = c
@@ -396,6 +424,7 @@ def run_b200(a):
             out = g_tab.cpu() if rank == 0 else None
             if rank == 0:
                 be.d2h_bytes += 8 * g_tab.numel()
+            torch.cuda.current_stream().synchronize()                           # this rank's downloads have landed
             return out
 
         e2e_step()
@@ -413,9 +442,18 @@ def run_b200(a):
         e2e_step()                                                   # untimed: counts the bytes one step moves
         sync_all()
         h2d, d2h = be.h2d_bytes, be.d2h_bytes
+        if world > 1:                                                # whole-job bytes: every rank's copies
+            bt = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+            dist.all_reduce(bt)
+            h2d, d2h = int(bt[0].item()), int(bt[1].item())
+        if sharded_io:
+            for b_ in (sh_vol, sh_bp, sh_proj):
+                b_.close()
         log("e2e done")
         e2e = {"value": updates_per_step / tt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": tt.item() * 1e3}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": tt.item() * 1e3,
+               "bytes_are": "summed over ranks", "host_buffers": "shared (POSIX shm, page-locked per rank): each rank moves 1/N"
+                                                               if sharded_io else "per-process pinned"}
 
     if rank == 0:
         cpu = None

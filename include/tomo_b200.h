@@ -82,6 +82,17 @@ TOMO_API size_t tomo_views_bytes(int n_proj);
  * staging copy is synchronised before return so `poses` may be reused immediately. */
 TOMO_API int tomo_views_upload(const TomoGeom* geom, const double* poses, int n_proj, void* views_dev, void* stream);
 
+/* Which kernel families a view table needs (host-side, from the table tomo_views_compute_host wrote).  Passing the mask to
+ * the *_ex / *_slab entry points lets them skip the launches that would find no view (each costs ~0.3 ms at 512^3: the
+ * kernel is launched over the full grid and every block leaves at once).  A mask computed for a table is also valid for any
+ * contiguous part of it.  0 = unknown: launch everything. */
+#define TOMO_KINDS_KNOWN       1     /* the mask is valid */
+#define TOMO_KINDS_GENERIC     2     /* tilted views: ray_kernel_forward / ray_kernel_gradient */
+#define TOMO_KINDS_SEPARABLE   4     /* untilted views (alpha = beta = 0): separable kernels */
+#define TOMO_KINDS_TILE        8     /* tilted views inside the scatter envelope: adjoint_tile_kernel */
+#define TOMO_KINDS_UNCOLOURED 16     /* views outside it (rays nearly parallel to z): adjoint_gather_kernel */
+TOMO_API int tomo_views_kinds(const double* views_host, int n_proj);
+
 /* ---- padded volume -------------------------------------------------------------------------- */
 /* The ray-driven kernels read a zero-bordered copy of the volume (zero-padded-corner semantics of
  * src/ray_wt_grad.f90:35-89 without per-corner branches): [nx+2P][ny+2P][nzp], nzp = nz+2P rounded
@@ -96,6 +107,10 @@ TOMO_API int tomo_pad_volume(const TomoGeom* geom, const float* vol_dev, float* 
  * (src/forward_projection.f90:1-68). */
 TOMO_API int tomo_forward(const TomoGeom* geom, const void* views_dev, int n_proj,
                  const float* volpad_dev, float* proj_dev, void* stream);
+
+/* tomo_forward with the table's TOMO_KINDS_* mask (see tomo_views_kinds). */
+TOMO_API int tomo_forward_ex(const TomoGeom* geom, const void* views_dev, int n_proj, int kinds,
+                    const float* volpad_dev, float* proj_dev, void* stream);
 
 /* vol (+)= A^T y, the exact transpose of tomo_forward: replaces
  * sparse.csc_matrix.dot(sparse.csr_matrix.transpose(A), y) (recon/sirt.py:61, recon/cgls.py:54,72).
@@ -112,6 +127,17 @@ TOMO_API size_t tomo_back_adjoint_workspace_bytes(const TomoGeom* geom, int n_pr
 TOMO_API int tomo_back_adjoint_ws(const TomoGeom* geom, const void* views_dev, int n_proj,
                          const float* proj_dev, float* vol_dev, int accumulate,
                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* tomo_back_adjoint_ws restricted to the x-slab [x_begin, x_end) of the volume (an x-slab of [nx][ny][nz] is contiguous):
+ * only voxels of the slab are written.  x_begin and x_end must be multiples of tomo_back_adjoint_slab_granularity()
+ * (x_end may also be nx).  Launching the slabs one after the other lets the caller start the all-reduce of slab k
+ * (recon/sirt_mpi.py:103) while slab k+1 is still being backprojected.  workspace_dev may be NULL (then untilted views take
+ * the tile kernel); with a workspace the slab that starts at x_begin = 0 must be launched first (it fills the z-transposed
+ * projections the later slabs read).  kinds: TOMO_KINDS_* mask or 0. */
+TOMO_API int tomo_back_adjoint_slab_granularity(void);
+TOMO_API int tomo_back_adjoint_slab(const TomoGeom* geom, const void* views_dev, int n_proj, int kinds,
+                           const float* proj_dev, float* vol_dev, int accumulate,
+                           void* workspace_dev, size_t workspace_bytes, int x_begin, int x_end, void* stream);
 
 /* Same operator and contract as tomo_back_adjoint, computed by the per-voxel gather kernel (an
  * independent formulation: ~8x slower, used as the cross-check of the tile-scatter kernel and for
@@ -166,6 +192,12 @@ TOMO_API int tomo_proj_grad(const TomoGeom* geom, const void* views_dev, int n_p
                    const float* volpad_dev, const float* meas_dev,
                    float* proj_dev, float* dproj_dev, double* grad6_dev, double* cost_dev,
                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* tomo_proj_grad with the table's TOMO_KINDS_* mask (see tomo_views_kinds). */
+TOMO_API int tomo_proj_grad_ex(const TomoGeom* geom, const void* views_dev, int n_proj, int kinds,
+                      const float* volpad_dev, const float* meas_dev,
+                      float* proj_dev, float* dproj_dev, double* grad6_dev, double* cost_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- TV proximal step ------------------------------------------------------ */
 /* Dual FISTA iteration of utilities/tv_denoise.py:98-170 (denoise_fista), two fused stencil kernels.

@@ -572,3 +572,48 @@ def test_operators_are_independent_on_the_gpu():
         assert rel_l2((A2.T @ yy).cpu().numpy(), r2.adjoint(yy.cpu().numpy().reshape(4, -1))) <= TOL_PROJ
         pm.projection_gradient(x.reshape(20, 20, 20), alpha[0], beta[0], phi[0], xyz[0], g.cor_shift[0])
     assert torch.equal(A1 @ x, y1)
+
+
+@pytest.mark.parametrize("tilt", [0.02, 0.0])
+def test_adjoint_in_x_slabs_equals_one_launch(tilt):
+    """tomo_back_adjoint_slab: the volume backprojected slab by slab (what the overlapped multi-GPU all-reduce does) is bitwise the
+    single launch -- tilted views (tile kernel), untilted views (separable adjoint: Yz filled by the first slab) and a mixed table."""
+    shape, dshape, n_proj = (90, 40, 64), (96, 64), 6
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, tilt=tilt, shift=2.0, seed=41)
+    if tilt:                                   # mixed table: two untilted views among the tilted ones
+        alpha[1] = beta[1] = alpha[4] = beta[4] = 0.0
+        be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+        op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
+    y = torch.rand((n_proj,) + dshape, device="cuda")
+    whole = be.adjoint(y)
+    assert rel_l2(whole.cpu().numpy(), op.adjoint(y.cpu().numpy())) <= TOL_PROJ
+    gx = be.slab_granularity()
+    assert gx == 20 and be.slabs(3) == [(0, 40), (40, 60), (60, 90)] and be.slabs(50) == [(0, 20), (20, 40), (40, 60), (60, 80), (80, 90)]
+    for n_slabs in (2, 3, 50):
+        out = torch.full(shape, 7.0, device="cuda")
+        for x0, x1 in be.slabs(n_slabs):
+            be.adjoint(y, out=out, x_range=(x0, x1))
+        assert torch.equal(out, whole)
+    with pytest.raises(Exception):
+        be.adjoint(y, out=torch.empty(shape, device="cuda"), x_range=(10, 40))        # not a tile-row boundary
+
+
+def test_view_kinds_skip_launches_without_changing_results():
+    """The TOMO_KINDS_* mask lets the operators skip kernels that would find no view; results equal the kinds = 0 path."""
+    from tomography_alignment_b200 import _lib
+    shape, dshape = (40, 36, 44), (40, 44)
+    for tilt, expect in ((0.0, _lib.load().tomo_version() and (1 | 4)), (0.03, 1 | 2 | 8)):
+        g, og, be, op, _ = setup(shape, dshape, 5, tilt=tilt, shift=1.0 if tilt else 0.0, seed=3)
+        assert be.kinds == expect
+        vol = torch.rand(shape, device="cuda")
+        y = torch.rand((5,) + dshape, device="cuda")
+        n0 = be.launches
+        f, b, gr = be.forward(vol), be.adjoint(y), be.proj_grad(vol, meas=y)
+        launched = be.launches - n0
+        kinds = be.kinds
+        be.kinds = 0                                  # unknown: every kernel is launched
+        n0 = be.launches
+        f0, b0, gr0 = be.forward(vol), be.adjoint(y), be.proj_grad(vol, meas=y)
+        assert be.launches - n0 > launched
+        be.kinds = kinds
+        assert torch.equal(f, f0) and torch.equal(b, b0) and torch.equal(gr["grad6"], gr0["grad6"]) and torch.equal(gr["dproj"], gr0["dproj"])

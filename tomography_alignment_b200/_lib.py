@@ -52,6 +52,16 @@ def load():
     L.tomo_views_bytes.argtypes = [ci]
     L.tomo_views_upload.restype = ci
     L.tomo_views_upload.argtypes = [G, vp, ci, vp, vp]
+    L.tomo_views_kinds.restype = ci
+    L.tomo_views_kinds.argtypes = [vp, ci]
+    L.tomo_forward_ex.restype = ci
+    L.tomo_forward_ex.argtypes = [G, vp, ci, ci, vp, vp, vp]
+    L.tomo_back_adjoint_slab_granularity.restype = ci
+    L.tomo_back_adjoint_slab_granularity.argtypes = []
+    L.tomo_back_adjoint_slab.restype = ci
+    L.tomo_back_adjoint_slab.argtypes = [G, vp, ci, ci, vp, vp, ci, vp, sz, ci, ci, vp]
+    L.tomo_proj_grad_ex.restype = ci
+    L.tomo_proj_grad_ex.argtypes = [G, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.tomo_padded_volume_bytes.restype = sz
     L.tomo_padded_volume_bytes.argtypes = [G]
     L.tomo_pad_volume.restype = ci

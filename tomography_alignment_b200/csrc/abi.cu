@@ -28,6 +28,20 @@ extern "C" size_t tomo_views_bytes(int n_proj)
     return n_proj > 0 ? sizeof(double) * TOMO_VIEW_STRIDE * (size_t)n_proj : 0;
 }
 
+extern "C" int tomo_views_kinds(const double* views_host, int n_proj)
+{
+    if (!views_host || n_proj <= 0) return 0;
+    int kinds = TOMO_KINDS_KNOWN;
+    for (int v = 0; v < n_proj; ++v) {
+        const double* V = views_host + (size_t)v * TOMO_VIEW_STRIDE;
+        const bool sep = V[V_SEP] != 0.0, col = V[V_NCOL] != 0.0;
+        kinds |= sep ? TOMO_KINDS_SEPARABLE : TOMO_KINDS_GENERIC;
+        if (!col) kinds |= TOMO_KINDS_UNCOLOURED;
+        else if (!sep) kinds |= TOMO_KINDS_TILE;
+    }
+    return kinds;
+}
+
 extern "C" int tomo_views_upload(const TomoGeom* g, const double* poses, int n_proj, void* views_dev, void* stream)
 {
     if (!views_dev) { tomo_set_error("tomo_views_upload: views_dev is NULL"); return TOMO_E_ARG; }

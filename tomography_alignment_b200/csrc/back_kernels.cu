@@ -58,6 +58,7 @@ struct BackArgs {
     int only_uncoloured;     // gather kernel: visit only the views the tile kernel skipped (V_NCOL == 0)
     int skip_separable;      // leave views with V_SEP == 1 to the separable adjoint (workspace variant)
     int only_vbig;           // voxel_bilinear: visit only the views the TMA kernel skipped (V_VBOK == 0)
+    int x_begin, x_end;      // adjoint kernels: the x-slab [x_begin, x_end) of the volume this launch writes
     double origin[3];        // voxel_bilinear only: the Fortran's origin argument
     double vox0[3], vpix[3]; // voxel_bilinear only: physical voxel centres = vox0 + idx*vpix
 };
@@ -67,8 +68,8 @@ adjoint_gather_kernel(const BackArgs A)
 {
     const int z = blockIdx.x * BZ + threadIdx.x;
     const int y = blockIdx.y * BY + threadIdx.y;
-    const int x = blockIdx.z * BX + threadIdx.z;
-    if (x >= A.nx || y >= A.ny || z >= A.nz) return;
+    const int x = A.x_begin + blockIdx.z * BX + threadIdx.z;
+    if (x >= A.x_end || y >= A.ny || z >= A.nz) return;
     const size_t n_det = (size_t)A.ndx * A.ndz;
     if (A.only_uncoloured && A.views[V_NUNCOL] == 0.0) return;      // every record holds the table's count
     float acc = 0.f;
@@ -457,7 +458,7 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     int bb = blockIdx.x;
     const int tz = bb % ntz; bb /= ntz;
     const int ty = bb % nty;
-    const int tx = bb / nty;
+    const int tx = bb / nty + A.x_begin / TX;             // slab launches start at a tile boundary
     const int org[3] = {tx * TX - 1, ty * TY - 1, tz * TZ - 1};   // voxel coordinate of smem cell 0 (the low ghost cell)
     // Nothing to scatter (every view of this table is left to the separable or the gather kernel): initialise the tile and leave,
     // instead of walking the view table in every block
@@ -472,7 +473,7 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
                 for (int i = threadIdx.x; i < TX * TY * 32; i += TNW * 32) {
                     const int zz = i & 31, yy = (i >> 5) % TY, xx = (i >> 5) / TY;
                     const int x = tx * TX + xx, y = ty * TY + yy, z = tz * TZ + zz;
-                    if (zz < TZ && x < A.nx && y < A.ny && z < A.nz) A.vol[((size_t)x * A.ny + y) * A.nz + z] = 0.f;
+                    if (zz < TZ && x < A.x_end && y < A.ny && z < A.nz) A.vol[((size_t)x * A.ny + y) * A.nz + z] = 0.f;
                 }
             return;
         }
@@ -508,7 +509,7 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     for (int i = threadIdx.x; i < TX * TY * 32; i += TNW * 32) {
         const int zz = i & 31, yy = (i >> 5) % TY, xx = (i >> 5) / TY;
         const int x = tx * TX + xx, y = ty * TY + yy, z = tz * TZ + zz;
-        if (zz < TZ && x < A.nx && y < A.ny && z < A.nz) {
+        if (zz < TZ && x < A.x_end && y < A.ny && z < A.nz) {
             const float v = acc[((xx + 1) * TSY + (yy + 1)) * TSZ + zz + 1];
             const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
             A.vol[vi] = A.accumulate ? A.vol[vi] + v : v;
@@ -575,6 +576,7 @@ static int fill_back(const TomoGeom* g, const void* views, int n_proj, const flo
     A->proj = proj; A->views = (const double*)views; A->vol = vol;
     A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz;
     A->n_proj = n_proj; A->accumulate = accumulate; A->only_uncoloured = 0; A->skip_separable = 0; A->only_vbig = 0;
+    A->x_begin = 0; A->x_end = g->nx;
     for (int a = 0; a < 3; ++a) { A->origin[a] = 0.0; A->vox0[a] = g->vox_origin[a]; A->vpix[a] = g->vox_pix[a]; }
     *grid = dim3((g->nz + BZ - 1) / BZ, (g->ny + BY - 1) / BY, (g->nx + BX - 1) / BX);
     if (grid->y > 65535u || grid->z > 65535u) { tomo_set_error("backprojector: volume too large for the launch grid"); return TOMO_E_RANGE; }
@@ -592,7 +594,7 @@ extern "C" int tomo_back_adjoint_gather(const TomoGeom* g, const void* views, in
 
 size_t tomo_back_separable_workspace_bytes(const TomoGeom* g, int n_proj);
 int tomo_back_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
-                               int accumulate, void* workspace, void* stream);
+                               int accumulate, void* workspace, int x_begin, int x_end, void* stream);
 
 extern "C" size_t tomo_back_adjoint_workspace_bytes(const TomoGeom* g, int n_proj)
 {
@@ -600,47 +602,76 @@ extern "C" size_t tomo_back_adjoint_workspace_bytes(const TomoGeom* g, int n_pro
     return tomo_back_separable_workspace_bytes(g, n_proj);
 }
 
-static int back_adjoint_impl(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
-                             int accumulate, void* workspace, size_t workspace_bytes, void* stream)
+// kinds: 0 = unknown (every kernel is launched and leaves at once when the table holds no view for it), otherwise the
+// TOMO_KINDS_* mask of tomo_views_kinds() for this table (or any table it is a part of): kernels without views are not launched.
+static int back_adjoint_impl(const TomoGeom* g, const void* views, int n_proj, int kinds, const float* proj, float* vol,
+                             int accumulate, void* workspace, size_t workspace_bytes, int x_begin, int x_end, void* stream)
 {
     BackArgs A; dim3 grid;
     if (int e = fill_back(g, views, n_proj, proj, vol, accumulate, &A, &grid)) return e;
+    constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
+    if (x_begin < 0 || x_end > g->nx || x_begin >= x_end || x_begin % TX != 0 || (x_end % TX != 0 && x_end != g->nx)) {
+        tomo_set_error("tomo_back_adjoint_slab: [x_begin, x_end) must be a non-empty range of whole tile rows "
+                       "(multiples of tomo_back_adjoint_slab_granularity(); x_end may also be nx)");
+        return TOMO_E_ARG;
+    }
     const bool sep = workspace != nullptr;
     if (sep && workspace_bytes < tomo_back_separable_workspace_bytes(g, n_proj)) {
         tomo_set_error("tomo_back_adjoint_ws: workspace too small (see tomo_back_adjoint_workspace_bytes)");
         return TOMO_E_WORKSPACE;
     }
+    const bool known = (kinds & TOMO_KINDS_KNOWN) != 0;
     A.skip_separable = sep ? 1 : 0;
-    constexpr int TX = TOMO_BT_X, TY = TOMO_BT_Y, TZ = TOMO_BT_Z;
-    const int ntx = (g->nx + TX - 1) / TX, nty = (g->ny + TY - 1) / TY, ntz = (g->nz + TZ - 1) / TZ;
+    A.x_begin = x_begin; A.x_end = x_end;
+    grid.z = (unsigned)((x_end - x_begin + BX - 1) / BX);
+    const int ntx = (x_end - x_begin + TX - 1) / TX, nty = (g->ny + TY - 1) / TY, ntz = (g->nz + TZ - 1) / TZ;
     const size_t smem = sizeof(float) * TSMEM_FLOATS;
     const double nblocks = (double)ntx * nty * ntz;
     if (nblocks >= 2147483647.0) { tomo_set_error("tomo_back_adjoint: too many tiles"); return TOMO_E_RANGE; }
-    cudaError_t ce = cudaFuncSetAttribute(adjoint_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (int e = tomo_check_cuda(ce, "cudaFuncSetAttribute(adjoint_tile_kernel)")) return e;
-    adjoint_tile_kernel<<<(unsigned)(ntx * nty * ntz), TNW * 32, smem, (cudaStream_t)stream>>>(A, ntx, nty, ntz);
-    if (int e = tomo_check_cuda(cudaGetLastError(), "adjoint_tile_kernel")) return e;
-    // views outside the scatter envelope (rays nearly parallel to z; none for tomographic poses): the
-    // gather kernel adds them; it returns at once when record 0 says there are none
-    A.only_uncoloured = 1; A.accumulate = 1;
-    adjoint_gather_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A);
-    if (int e = tomo_check_cuda(cudaGetLastError(), "adjoint_gather_kernel(uncoloured)")) return e;
-    // untilted views: separable adjoint (needs the Yz workspace); it returns at once for tilted views
-    if (sep) return tomo_back_separable_launch(g, views, n_proj, proj, vol, 1, workspace, stream);
+    // tilted views inside the scatter envelope (and, without a workspace, the untilted ones): the tile kernel.  It writes
+    // every voxel of the slab, so the kernels after it accumulate; when it is not needed the first kernel launched
+    // inherits the caller's accumulate flag.
+    const bool want_tile = !known || (kinds & TOMO_KINDS_TILE) || (!sep && (kinds & TOMO_KINDS_SEPARABLE));
+    const bool want_gather = !known || (kinds & TOMO_KINDS_UNCOLOURED);
+    const bool want_sep = sep && (!known || (kinds & TOMO_KINDS_SEPARABLE));
+    if (want_tile || !(want_gather || want_sep)) {
+        cudaError_t ce = cudaFuncSetAttribute(adjoint_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (int e = tomo_check_cuda(ce, "cudaFuncSetAttribute(adjoint_tile_kernel)")) return e;
+        adjoint_tile_kernel<<<(unsigned)(ntx * nty * ntz), TNW * 32, smem, (cudaStream_t)stream>>>(A, ntx, nty, ntz);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "adjoint_tile_kernel")) return e;
+        accumulate = 1;
+    }
+    // views outside the scatter envelope (rays nearly parallel to z; none for tomographic poses): the gather kernel
+    if (want_gather) {
+        A.only_uncoloured = 1; A.accumulate = accumulate;
+        adjoint_gather_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "adjoint_gather_kernel(uncoloured)")) return e;
+        accumulate = 1;
+    }
+    // untilted views: separable adjoint (needs the Yz workspace, filled by the launch of the slab that starts at x = 0)
+    if (want_sep) return tomo_back_separable_launch(g, views, n_proj, proj, vol, accumulate, workspace, x_begin, x_end, stream);
     return 0;
+}
+
+extern "C" int tomo_back_adjoint_slab_granularity(void) { return TOMO_BT_X; }
+
+extern "C" int tomo_back_adjoint_slab(const TomoGeom* g, const void* views, int n_proj, int kinds, const float* proj, float* vol,
+                                      int accumulate, void* workspace, size_t workspace_bytes, int x_begin, int x_end, void* stream)
+{
+    return back_adjoint_impl(g, views, n_proj, kinds, proj, vol, accumulate, workspace, workspace_bytes, x_begin, x_end, stream);
 }
 
 extern "C" int tomo_back_adjoint(const TomoGeom* g, const void* views, int n_proj,
                                  const float* proj, float* vol, int accumulate, void* stream)
 {
-    return back_adjoint_impl(g, views, n_proj, proj, vol, accumulate, nullptr, 0, stream);
+    return back_adjoint_impl(g, views, n_proj, 0, proj, vol, accumulate, nullptr, 0, 0, g ? g->nx : 0, stream);
 }
 
 extern "C" int tomo_back_adjoint_ws(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
                                     int accumulate, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (!workspace) { tomo_set_error("tomo_back_adjoint_ws: workspace is NULL"); return TOMO_E_ARG; }
-    return back_adjoint_impl(g, views, n_proj, proj, vol, accumulate, workspace, workspace_bytes, stream);
+    return back_adjoint_impl(g, views, n_proj, 0, proj, vol, accumulate, workspace, workspace_bytes, 0, g ? g->nx : 0, stream);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point table (the library does not link libcuda).

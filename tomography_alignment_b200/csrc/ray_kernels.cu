@@ -212,16 +212,26 @@ static int fill_args(const TomoGeom* g, const void* views, int n_proj, const flo
 extern "C" int tomo_forward(const TomoGeom* g, const void* views, int n_proj,
                             const float* volpad, float* proj, void* stream)
 {
+    return tomo_forward_ex(g, views, n_proj, 0, volpad, proj, stream);
+}
+
+extern "C" int tomo_forward_ex(const TomoGeom* g, const void* views, int n_proj, int kinds,
+                               const float* volpad, float* proj, void* stream)
+{
     RayArgs A;
     if (int e = fill_args(g, views, n_proj, volpad, &A)) return e;
     if (!proj) { tomo_set_error("tomo_forward: proj_dev is NULL"); return TOMO_E_ARG; }
     A.proj = proj;
     A.skip_separable = 1;
+    const bool known = (kinds & TOMO_KINDS_KNOWN) != 0;
     const dim3 block(TILE_Z, TILE_X);
-    ray_kernel_forward<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
-    if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward")) return e;
+    if (!known || (kinds & TOMO_KINDS_GENERIC)) {
+        ray_kernel_forward<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward")) return e;
+    }
     // untilted views (alpha = beta = 0): separable kernel; both kernels return at once for views of the other kind
-    return tomo_forward_separable_launch(g, views, n_proj, volpad, proj, stream);
+    if (!known || (kinds & TOMO_KINDS_SEPARABLE)) return tomo_forward_separable_launch(g, views, n_proj, volpad, proj, stream);
+    return 0;
 }
 
 extern "C" size_t tomo_proj_grad_workspace_bytes(const TomoGeom* g, int n_proj)
@@ -239,6 +249,14 @@ extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
                               float* proj, float* dproj, double* grad6, double* cost,
                               void* workspace, size_t workspace_bytes, void* stream)
 {
+    return tomo_proj_grad_ex(g, views, n_proj, 0, volpad, meas, proj, dproj, grad6, cost, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tomo_proj_grad_ex(const TomoGeom* g, const void* views, int n_proj, int kinds,
+                                 const float* volpad, const float* meas,
+                                 float* proj, float* dproj, double* grad6, double* cost,
+                                 void* workspace, size_t workspace_bytes, void* stream)
+{
     RayArgs A;
     if (int e = fill_args(g, views, n_proj, volpad, &A)) return e;
     A.meas = meas; A.proj = proj; A.dproj = dproj;
@@ -252,18 +270,25 @@ extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
         A.partial = (double*)workspace;
     }
     A.skip_separable = 1;
+    const bool known = (kinds & TOMO_KINDS_KNOWN) != 0;
+    const bool want_gen = !known || (kinds & TOMO_KINDS_GENERIC), want_sep = !known || (kinds & TOMO_KINDS_SEPARABLE);
     const dim3 block(TILE_Z, TILE_X);
-    ray_kernel_gradient<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
-    if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_gradient")) return e;
+    if (want_gen) {
+        ray_kernel_gradient<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_gradient")) return e;
+    }
     // untilted views: separable kernel with its own block partials behind the generic ones
     double* sep_partial = reduce ? A.partial + (size_t)NRED * A.nxt * A.nzt * n_proj : nullptr;
-    if (int e = tomo_grad_separable_launch(g, views, n_proj, volpad, meas, proj, dproj, sep_partial, stream)) return e;
+    if (want_sep)
+        if (int e = tomo_grad_separable_launch(g, views, n_proj, volpad, meas, proj, dproj, sep_partial, stream)) return e;
     if (reduce) {
         const int n = n_proj * NRED;
         int sxt, sch;
         tomo_grad_separable_tiles(g, &sxt, &sch);
-        grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, A.views, 0, n_proj, A.nxt, A.nzt, grad6, cost);
-        grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sep_partial, A.views, 1, n_proj, sxt, sch, grad6, cost);
+        if (want_gen)
+            grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, A.views, 0, n_proj, A.nxt, A.nzt, grad6, cost);
+        if (want_sep)
+            grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sep_partial, A.views, 1, n_proj, sxt, sch, grad6, cost);
         return tomo_check_cuda(cudaGetLastError(), "grad_finalize_kernel");
     }
     return 0;

@@ -200,6 +200,7 @@ struct SepBackArgs {
     float*        yz;        // workspace [n_proj][ndx][nzw]
     float*        vol;
     int nx, ny, nz, ndx, ndz, n_proj, nzw, accumulate;
+    int x_begin, x_end;      // x-slab of the volume this launch writes
 };
 
 // Yz[view][ix][z] (z-transpose of the 2-tap interpolation) for the separable views of the table
@@ -223,8 +224,8 @@ sep_adjoint_kernel(const SepBackArgs A)
 {
     const int lane = threadIdx.x;
     if (A.views[V_NSEP] == 0.0) return;                               // no untilted view in the table
-    const int x = blockIdx.y * SA_WARPS_X + threadIdx.z, y = blockIdx.x * SA_WARPS_Y + threadIdx.y;
-    if (x >= A.nx || y >= A.ny) return;                               // whole warp
+    const int x = A.x_begin + blockIdx.y * SA_WARPS_X + threadIdx.z, y = blockIdx.x * SA_WARPS_Y + threadIdx.y;
+    if (x >= A.x_end || y >= A.ny) return;                            // whole warp
     const int zbase = blockIdx.z * (128 * SA_QPL);
     f2 acc[SA_QPL][2];
 #pragma unroll
@@ -301,17 +302,20 @@ size_t tomo_back_separable_workspace_bytes(const TomoGeom* g, int n_proj)
 
 // vol (+)= A^T y restricted to the separable views of the table (the caller has already handled the others)
 int tomo_back_separable_launch(const TomoGeom* g, const void* views, int n_proj, const float* proj, float* vol,
-                               int accumulate, void* workspace, void* stream)
+                               int accumulate, void* workspace, int x_begin, int x_end, void* stream)
 {
     SepBackArgs A;
     A.proj = proj; A.views = (const double*)views; A.yz = (float*)workspace; A.vol = vol;
     A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
     A.nzw = ((g->nz + 3) / 4) * 4;
     A.accumulate = accumulate;
+    A.x_begin = x_begin; A.x_end = x_end;
     const double nrows = (double)g->ndx * n_proj;
-    sep_zgather_kernel<<<(unsigned)(nrows < 148.0 * 32 ? nrows : 148.0 * 32), 256, 0, (cudaStream_t)stream>>>(A);
-    if (int e = tomo_check_cuda(cudaGetLastError(), "sep_zgather_kernel")) return e;
-    const dim3 grid((g->ny + SA_WARPS_Y - 1) / SA_WARPS_Y, (g->nx + SA_WARPS_X - 1) / SA_WARPS_X,
+    if (x_begin == 0) {      // Yz does not depend on the slab: the launch of the first slab fills it for the ones that follow
+        sep_zgather_kernel<<<(unsigned)(nrows < 148.0 * 32 ? nrows : 148.0 * 32), 256, 0, (cudaStream_t)stream>>>(A);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "sep_zgather_kernel")) return e;
+    }
+    const dim3 grid((g->ny + SA_WARPS_Y - 1) / SA_WARPS_Y, (x_end - x_begin + SA_WARPS_X - 1) / SA_WARPS_X,
                     (A.nzw + 128 * SA_QPL - 1) / (128 * SA_QPL));
     if (grid.y > 65535u || grid.z > 65535u) { tomo_set_error("separable adjoint: volume too large for the launch grid"); return TOMO_E_RANGE; }
     sep_adjoint_kernel<<<grid, dim3(32, SA_WARPS_Y, SA_WARPS_X), 0, (cudaStream_t)stream>>>(A);

@@ -33,6 +33,7 @@ class CudaBackend(object):
         self.det_shape = tuple(int(v) for v in geometry.det_shape)
         self.n_det = self.det_shape[0] * self.det_shape[1]
         self.n_proj = 0
+        self.kinds = 0           # TOMO_KINDS_* mask of the current view table (0: unknown)
         self.views = None
         self._volpad = None
         self._ws = None
@@ -122,20 +123,36 @@ class CudaBackend(object):
         poses = full_pose_table(self.geometry, poses)
         n = poses.shape[0]
         # always a fresh table: operators returned by earlier projection_matrix() calls keep (and re-bind) theirs
-        self.views = torch.empty((n, _lib.VIEW_STRIDE), dtype=torch.float64, device=self.device)
+        host = np.empty((n, _lib.VIEW_STRIDE), dtype=np.float64)
+        rc = self.lib.tomo_views_compute_host(self._g(), poses.ctypes.data_as(ctypes.c_void_p), n,
+                                              host.ctypes.data_as(ctypes.c_void_p))
+        _lib.check(rc, "tomo_views_compute_host")
+        # which kernel families this table needs: the operators then skip the launches that would find no view
+        self.kinds = int(self.lib.tomo_views_kinds(host.ctypes.data_as(ctypes.c_void_p), n))
+        self.views = torch.as_tensor(host).to(self.device)
         self._bound_state = None
-        with torch.cuda.device(self.device):
-            rc = self.lib.tomo_views_upload(self._g(), poses.ctypes.data_as(ctypes.c_void_p), n, _ptr(self.views),
-                                            self._stream())
-        _lib.check(rc, "tomo_views_upload")
         self.n_proj = n
 
-    def bind_views(self, views, n_proj):
+    def bind_views(self, views, n_proj, kinds=0):
         """Make a view table uploaded by an earlier set_poses() the current one again (ProjectionOperator._bind)."""
         if views.device != self.device or views.dtype != torch.float64 or tuple(views.shape) != (n_proj, _lib.VIEW_STRIDE):
             raise ValueError("bind_views: not a view table of this backend")
         self.views = views
         self.n_proj = int(n_proj)
+        self.kinds = int(kinds)
+
+    def _count(self, op):
+        """Kernels one call of ``op`` launches for the current table (bench.py reports the total)."""
+        k = self.kinds
+        gen, sep = bool(k & 2) or not k, bool(k & 4) or not k
+        if op == "forward":
+            return int(gen) + int(sep)
+        if op == "adjoint":
+            tile = bool(k & 8) or not k
+            return int(tile) + int(bool(k & 16) or not k) + 2 * int(sep)
+        if op == "grad":
+            return int(gen) + int(sep)
+        return (int(gen) + int(sep)) * 2            # grad + finalize passes
 
     # -- operators -----------------------------------------------------------------------------
     def pad(self, vol):
@@ -158,14 +175,18 @@ class CudaBackend(object):
         else:
             self._check_out(out, (self.n_proj,) + self.det_shape, "forward")
         with torch.cuda.device(self.device):
-            rc = self.lib.tomo_forward(self._g(), _ptr(self.views), self.n_proj, _ptr(volpad), _ptr(out), self._stream())
+            rc = self.lib.tomo_forward_ex(self._g(), _ptr(self.views), self.n_proj, self.kinds, _ptr(volpad), _ptr(out),
+                                          self._stream())
         _lib.check(rc, "tomo_forward")
-        self.launches += 2       # ray_kernel_forward + sep_forward_kernel (each skips the other's views)
+        self.launches += self._count("forward")
         return out
 
-    def adjoint(self, y, out=None, accumulate=False, gather=False):
+    def adjoint(self, y, out=None, accumulate=False, gather=False, x_range=None):
         """vol (+)= A^T y: float32 (nx, ny, nz) on the device.  ``gather=True`` uses the per-voxel gather
-        kernel (tomo_back_adjoint_gather), the independent formulation kept as a cross-check."""
+        kernel (tomo_back_adjoint_gather), the independent formulation kept as a cross-check.
+        ``x_range=(x0, x1)`` writes only the x-slab [x0, x1) of ``out`` (still the full-volume tensor; multiples of
+        ``slab_granularity()``, slabs issued in ascending order from 0): the caller can all-reduce a finished slab
+        while the next one is computed."""
         y = self._as_proj(y)
         if out is None:
             out = torch.empty(self.vol_shape, dtype=torch.float32, device=self.device)
@@ -178,11 +199,22 @@ class CudaBackend(object):
                                                        int(bool(accumulate)), self._stream())
             else:
                 ws, nbytes = self._back_ws(self.n_proj)
-                rc = self.lib.tomo_back_adjoint_ws(self._g(), _ptr(self.views), self.n_proj, _ptr(y), _ptr(out),
-                                                   int(bool(accumulate)), _ptr(ws), nbytes, self._stream())
+                x0, x1 = (0, self.vol_shape[0]) if x_range is None else (int(x_range[0]), int(x_range[1]))
+                rc = self.lib.tomo_back_adjoint_slab(self._g(), _ptr(self.views), self.n_proj, self.kinds, _ptr(y), _ptr(out),
+                                                     int(bool(accumulate)), _ptr(ws), nbytes, x0, x1, self._stream())
         _lib.check(rc, "tomo_back_adjoint")
-        self.launches += 1 if gather else 4   # tile + gather(uncoloured) + sep_zgather + sep_adjoint
+        self.launches += 1 if gather else self._count("adjoint")
         return out
+
+    def slab_granularity(self):
+        return int(self.lib.tomo_back_adjoint_slab_granularity())
+
+    def slabs(self, n_slabs):
+        """``n_slabs`` x-ranges of whole tile rows covering the volume (fewer when the volume has fewer tile rows)."""
+        gx, nx = self.slab_granularity(), self.vol_shape[0]
+        rows = (nx + gx - 1) // gx
+        cuts = sorted(set(int(round(k * rows / float(max(1, n_slabs)))) for k in range(max(1, n_slabs) + 1)))
+        return [(a * gx, min(nx, b * gx)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
     # -- host-buffer entry points: copies overlapped with the kernels in view chunks ------------------
     def forward_host(self, x_host, out_host=None, chunk_views=None, vol_dev=None):
@@ -214,9 +246,10 @@ class CudaBackend(object):
         proj_d = self._buf("proj", (self.n_proj,) + self.det_shape)
         with torch.cuda.device(self.device):
             for a, b in self._chunks(chunk_views):
-                rc = self.lib.tomo_forward(self._g(), self._views_at(a), b - a, _ptr(volpad), _ptr(proj_d[a:b]), self._stream())
+                rc = self.lib.tomo_forward_ex(self._g(), self._views_at(a), b - a, self.kinds, _ptr(volpad), _ptr(proj_d[a:b]),
+                                              self._stream())
                 _lib.check(rc, "tomo_forward")
-                self.launches += 2
+                self.launches += self._count("forward")
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 with torch.cuda.stream(cp):
@@ -242,7 +275,7 @@ class CudaBackend(object):
             out_host = torch.empty(self.vol_shape, dtype=torch.float32, pin_memory=True)
         cur, cp = torch.cuda.current_stream(self.device), self._copy_stream()
         y_d = self._buf("proj", (self.n_proj,) + self.det_shape).reshape(self.n_proj, -1)
-        vol_d = self._buf("vol", self.vol_shape)
+        vol_d = self._buf("bp", self.vol_shape)          # not "vol": the volume forward_host uploaded stays valid
         chunks = self._chunks(chunk_views)
         ws, ws_bytes = self._back_ws(max(b - a for a, b in chunks))
         cp.wait_stream(cur)                      # y_d / vol_d may still be in use by earlier work on `cur`
@@ -256,10 +289,10 @@ class CudaBackend(object):
         with torch.cuda.device(self.device):
             for k, (a, b) in enumerate(chunks):
                 cur.wait_event(evs[k])
-                rc = self.lib.tomo_back_adjoint_ws(self._g(), self._views_at(a), b - a, _ptr(y_d[a:b]), _ptr(vol_d),
-                                                   int(k > 0), _ptr(ws), ws_bytes, self._stream())
+                rc = self.lib.tomo_back_adjoint_slab(self._g(), self._views_at(a), b - a, self.kinds, _ptr(y_d[a:b]), _ptr(vol_d),
+                                                     int(k > 0), _ptr(ws), ws_bytes, 0, self.vol_shape[0], self._stream())
                 _lib.check(rc, "tomo_back_adjoint")
-                self.launches += 4
+                self.launches += self._count("adjoint")
         self.h2d_bytes += 4 * y_host.numel()
         if not to_host:
             cp.synchronize()                     # the pinned input may be reused by the caller from here on
@@ -307,10 +340,11 @@ class CudaBackend(object):
         with torch.cuda.device(self.device):
             for k, (a, b) in enumerate(chunks):
                 cur.wait_event(evs[k])
-                rc = self.lib.tomo_proj_grad(self._g(), self._views_at(a), b - a, _ptr(volpad), _ptr(m_d[a:b]), None, None,
-                                             _ptr(grad6[a:b]), _ptr(cost[a:b]), _ptr(self._ws), ws_bytes, self._stream())
+                rc = self.lib.tomo_proj_grad_ex(self._g(), self._views_at(a), b - a, self.kinds, _ptr(volpad), _ptr(m_d[a:b]),
+                                                None, None, _ptr(grad6[a:b]), _ptr(cost[a:b]), _ptr(self._ws), ws_bytes,
+                                                self._stream())
                 _lib.check(rc, "tomo_proj_grad")
-                self.launches += 2
+                self.launches += self._count("grad6")
         self.h2d_bytes += 4 * meas_host.numel()
         if not to_host:
             cp.synchronize()                     # uploads of the pinned inputs are complete
@@ -376,9 +410,9 @@ class CudaBackend(object):
             if self._ws is None or self._ws.numel() * 8 < ws_bytes:
                 self._ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            rc = self.lib.tomo_proj_grad(self._g(), _ptr(self.views), n, _ptr(volpad), _ptr(meas), _ptr(proj), _ptr(dproj),
-                                         _ptr(grad6), _ptr(cost), _ptr(self._ws) if want_grad6 else None,
-                                         ws_bytes, self._stream())
+            rc = self.lib.tomo_proj_grad_ex(self._g(), _ptr(self.views), n, self.kinds, _ptr(volpad), _ptr(meas), _ptr(proj),
+                                            _ptr(dproj), _ptr(grad6), _ptr(cost), _ptr(self._ws) if want_grad6 else None,
+                                            ws_bytes, self._stream())
         _lib.check(rc, "tomo_proj_grad")
-        self.launches += 4 if want_grad6 else 2   # ray + separable gradient kernels (+ two finalize passes)
+        self.launches += self._count("grad6" if want_grad6 else "grad")
         return {"proj": proj, "dproj": dproj, "grad6": grad6, "cost": cost}

@@ -187,10 +187,11 @@ class ProjectionOperator(object):
         if self._poses is None or getattr(b, "_bound_state", None) is self._state:
             return
         if self._state["views"] is not None and hasattr(b, "bind_views"):
-            b.bind_views(self._state["views"], self._n_proj)
+            b.bind_views(self._state["views"], self._n_proj, self._state.get("kinds", 0))
         else:
             b.set_poses(self._poses)
             self._state["views"] = getattr(b, "views", None)
+            self._state["kinds"] = getattr(b, "kinds", 0)
         b._bound_state = self._state
 
     def _mask_on(self, like):
@@ -267,7 +268,7 @@ class ProjectionMatrix(object):
         poses = pose_table(self.angles, self.xyz_shift, cor[:self.n_proj])
         backend = self._get_backend()
         backend.set_poses(poses)
-        state = {"views": getattr(backend, "views", None)}
+        state = {"views": getattr(backend, "views", None), "kinds": getattr(backend, "kinds", 0)}
         backend._bound_state = state
         mask, all_masked = None, False
         if voxel_mask is not None:

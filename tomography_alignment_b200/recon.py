@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 from .projection_operators import ProjectionMatrix, normalise_poses, pose_table
-from .sharding import shard_views
+from .sharding import adjoint_allreduce, check_world, shard_views
 
 
 class _DeviceSolver(object):
@@ -29,9 +29,12 @@ class _DeviceSolver(object):
         self.n_proj = self.angles.shape[0]
         self.precision = options['precision'] if 'precision' in options else np.float32
         self.voxel_mask = options['voxel_mask'] if 'voxel_mask' in options else None
+        # views are sharded only when a process group is passed explicitly: group=None is an independent per-rank
+        # reconstruction even inside a torchrun job
         self.group = group
-        self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        self.world = dist.get_world_size(group) if group is not None else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        check_world(self.n_proj, self.world)
         self.my_index = shard_views(self.n_proj, self.world, self.rank)
         self.my_n_proj = int(len(self.my_index))
         if backend is None:
@@ -59,9 +62,10 @@ class _DeviceSolver(object):
         return self.backend.forward(x).reshape(self.my_n_proj, -1)
 
     def _At(self, y):
-        v = self.backend.adjoint(y).reshape(-1)
-        if self.world > 1:
-            dist.all_reduce(v, group=self.group)
+        v, works = adjoint_allreduce(self.backend, y, None, self.group, reduce=self.world > 1)
+        for w in works:                   # slab all-reduces queued behind their kernels (sharding.adjoint_allreduce)
+            w.wait()
+        v = v.reshape(-1)
         if self.mask is not None:
             v = v * self.mask
         return v

@@ -23,6 +23,72 @@ def shard_views(n_proj, world, rank):
     return np.array_split(np.arange(n_proj), world)[rank]
 
 
+def check_world(n_proj, world):
+    """Every rank must own at least one view: a rank with an empty shard would raise on its own while its peers wait in
+    the next collective.  All ranks know n_proj and the world size, so all of them raise together."""
+    if world > n_proj:
+        raise ValueError("%d ranks for %d views: every rank needs at least one view (use a smaller process group)"
+                         % (world, n_proj))
+
+
+def adjoint_allreduce(backend, y_local, out=None, group=None, n_slabs=8, reduce=True):
+    """vol = sum over ranks of A_rank^T y_rank with the collective hidden behind the kernel: the volume is backprojected in
+    ``n_slabs`` x-slabs (tomo_back_adjoint_slab; an x-slab of [nx][ny][nz] is contiguous) and the all-reduce of slab k is
+    queued asynchronously as soon as its kernel is, so NCCL sums slab k over NVLink while slab k+1 is computed.
+    Replaces the blocking comm.Allreduce(my_back_proj, rec) of recon/sirt_mpi.py:103.
+    Returns (volume, works); the volume is complete once every ``work.wait()`` has been called (stream-ordered, the host
+    does not block).  ``group=None`` is the default process group; ``reduce=False``: no collective, one launch."""
+    reduce = reduce and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not reduce or not hasattr(backend, "slabs"):
+        v = backend.adjoint(y_local, out=out)
+        if reduce:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+        return v, []
+    if out is None:
+        out = torch.empty(backend.vol_shape, dtype=torch.float32, device=backend.device)
+    vol3 = out.reshape(backend.vol_shape)
+    works = []
+    for x0, x1 in backend.slabs(n_slabs):
+        backend.adjoint(y_local, out=out, x_range=(x0, x1))
+        works.append(dist.all_reduce(vol3[x0:x1], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return out, works
+
+
+class SharedHostBuffer(object):
+    """A host array all ranks of the box see (POSIX shared memory), page-locked in every process so that each rank's
+    device<->host copies into its own part are asynchronous.  The single-box counterpart of what the reference's MPI scripts
+    do with Allreduce / Gather into rank 0's numpy arrays (examples/mpi_reconstruct.py:41): each rank moves only its 1/N of
+    the bytes over its own PCIe link and rank 0 (or any rank) reads the whole array from host memory."""
+
+    def __init__(self, name, shape, dtype=torch.float32, group=None):
+        import os
+        self.path = os.path.join("/dev/shm", name)
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        n = int(np.prod(shape))
+        if rank == 0:
+            if os.path.exists(self.path):
+                os.remove(self.path)
+            t = torch.from_file(self.path, shared=True, size=n, dtype=dtype)
+        if dist.is_initialized():
+            dist.barrier(group)
+        if rank != 0:
+            t = torch.from_file(self.path, shared=True, size=n, dtype=dtype)
+        self.tensor = t.reshape(shape)
+        self.pinned = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+            self.pinned = int(rc) == 0
+        self._owner = rank == 0
+
+    def close(self):
+        import os
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.pinned = False
+        if self._owner and os.path.exists(self.path):
+            os.remove(self.path)
+
+
 class ShardedProjector(object):
     """A, A^T and the per-view gradient with views sharded over the ranks of ``group``.
 
@@ -40,6 +106,7 @@ class ShardedProjector(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.geometry = geometry
         self.n_proj, angles, xyz = normalise_poses(geometry, alpha, beta, phi, xyz_shift)
+        check_world(self.n_proj, self.world)
         self.my_index = shard_views(self.n_proj, self.world, self.rank)
         self.my_n_proj = int(np.size(self.my_index))
         self.angles, self.xyz_shift = angles, xyz
@@ -47,9 +114,7 @@ class ShardedProjector(object):
         self._my_cor = cor[self.my_index]
         backend = backend_factory(geometry) if backend_factory is not None else None
         self.pm = ProjectionMatrix(geometry, precision=precision, device=device, backend=backend)
-        self.op = None
-        if self.my_n_proj > 0:
-            self._set_local_poses()
+        self._set_local_poses()
 
     def _set_local_poses(self):
         # projection_matrix reads geometry.cor_shift[:n]; hand it this rank's rows for the call
@@ -69,12 +134,22 @@ class ShardedProjector(object):
 
     def forward(self, vol):
         """Local rows of A vol (torch tensor in -> torch tensor out on the same device)."""
+        self.op._bind()
         return self.op._backend.forward(vol)
 
-    def adjoint(self, y_local, out=None):
-        """sum over ranks of A_rank^T y_rank, replicated on every rank (sirt_mpi.py:101-103)."""
-        v = self.op._backend.adjoint(y_local, out=out)
-        return self._allreduce(v)
+    def adjoint(self, y_local, out=None, n_slabs=8, wait=True):
+        """sum over ranks of A_rank^T y_rank, replicated on every rank (sirt_mpi.py:101-103).
+
+        The volume is backprojected in x-slabs and the all-reduce of a finished slab runs (on NCCL's stream, over NVLink)
+        while the next slab is computed (``adjoint_allreduce``).  ``wait=False`` returns ``(volume, works)`` so the caller
+        can queue independent kernels before ``for w in works: w.wait()``."""
+        self.op._bind()
+        v, works = adjoint_allreduce(self.op._backend, y_local, out, self.group, n_slabs, reduce=self.world > 1)
+        if not wait:
+            return v, works
+        for w in works:
+            w.wait()
+        return v
 
     def residual_norm2(self, res_local):
         """sum over ranks of ||res||^2 as a float64 scalar tensor (sirt_mpi.py:110)."""
@@ -84,7 +159,8 @@ class ShardedProjector(object):
     def proj_grad(self, vol, meas_local, want_dproj=False):
         """Per-view 6-DOF gradients of all views on every rank: local views are computed, written into a
         zero (n_proj, 7) float64 table at their global rows, and the table is all-reduced."""
-        be = self.pm._get_backend()
+        self.op._bind()
+        be = self.op._backend
         out = be.proj_grad(vol, meas=meas_local, want_proj=True, want_dproj=want_dproj)
         table = torch.zeros((self.n_proj, 7), dtype=torch.float64, device=out["grad6"].device)
         idx = torch.as_tensor(self.my_index, device=table.device, dtype=torch.long)
