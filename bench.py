@@ -66,7 +66,9 @@ def parse():
     ap.add_argument("--cpu-size", type=int, default=256, help="volume size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--slabs", type=int, default=8, help="x-slabs of the backprojection (all-reduce of slab k under the kernel of slab k+1)")
+    ap.add_argument("--slabs", type=int, default=1,
+                    help="x-slabs of the backprojection (all-reduce of slab k under the kernel of slab k+1); 1 = one launch on a side "
+                         "stream, its all-reduce hidden behind the gradient kernel (measured best: profiles/README.md)")
     ap.add_argument("--host-phantom", action="store_true",
                     help="build the phantom with numpy on the host (profiling runs: keeps torch's phantom kernels out of ncu launch lists)")
     return ap.parse_args()
@@ -401,22 +403,26 @@ def run_b200(a):
             # host buffers in, host buffers out; copies are issued inside the calls (view chunks, side stream)
             if world == 1:
                 be.forward_host(h_vol, out_host=h_proj)                         # H2D volume, forward, D2H projections
-                be.adjoint_host(h_meas, out_host=h_bp)                          # H2D projections, adjoint, D2H volume
-                return be.proj_grad_host(None, h_meas, vol_dev=be._buf("vol", be.vol_shape))   # H2D measured, D2H (n, 6) gradients
+                be.adjoint_host(h_meas, out_host=h_bp, wait=False)              # H2D projections, adjoint, D2H volume (queued)
+                out = be.proj_grad_host(None, h_meas, vol_dev=be._buf("vol", be.vol_shape))   # H2D measured, D2H (n, 6) gradients
+                be.sync_host()                                                  # the volume download (under the gradient kernel) has landed
+                return out
             dv = upload_volume()                                                # H2D volume: once per step, 1/N per rank
             out_rows = sh_proj.tensor[mine[0]:mine[-1] + 1] if sharded_io else h_proj
             be.forward_host(None, out_host=out_rows, vol_dev=dv)                # forward, D2H of this rank's views
             v = be.adjoint_host(h_meas, out_host=None, to_host=False)           # H2D projections, adjoint (device volume)
             if sharded_io:                                                      # reduce-scatter instead of the Allreduce of
-                dist.reduce_scatter_tensor(bp_slab, v)                          # recon/sirt_mpi.py:103: each rank downloads
-                sh_bp.tensor[my_x].copy_(bp_slab, non_blocking=True)            # its summed x-slab into the shared buffer
-                be.d2h_bytes += 4 * bp_slab.numel()
+                rs = dist.reduce_scatter_tensor(bp_slab, v, async_op=True)      # recon/sirt_mpi.py:103, under the gradient kernel
             else:
                 dist.all_reduce(v)
                 if rank == 0:
                     h_bp.copy_(v)
                     be.d2h_bytes += 4 * v.numel()
             g6, c = be.proj_grad_host(None, h_meas, vol_dev=dv, to_host=False)
+            if sharded_io:                                                      # each rank downloads its summed x-slab into
+                rs.wait()                                                       # the shared host buffer
+                sh_bp.tensor[my_x].copy_(bp_slab, non_blocking=True)
+                be.d2h_bytes += 4 * bp_slab.numel()
             g_tab.zero_()
             g_tab[idx, :6] = g6
             g_tab[idx, 6] = c

@@ -112,7 +112,9 @@ class CudaBackend(object):
         return t.contiguous()
 
     def _chunks(self, chunk_views):
-        c = max(1, int(chunk_views) if chunk_views else max(1, (self.n_proj + 7) // 8))
+        # default: up to 8 chunks, but no chunk below 32 views (every launch pays its wave tail and, for the adjoint, one
+        # read-modify-write pass over the volume)
+        c = max(1, int(chunk_views) if chunk_views else max(32, (self.n_proj + 7) // 8))
         return [(a, min(self.n_proj, a + c)) for a in range(0, self.n_proj, c)]
 
     # -- poses ---------------------------------------------------------------------------------
@@ -206,6 +208,12 @@ class CudaBackend(object):
         self.launches += 1 if gather else self._count("adjoint")
         return out
 
+    def slab_streams(self):
+        """Two side streams the slab launches of the overlapped multi-GPU backprojection alternate between."""
+        if getattr(self, "_slab_pool", None) is None:
+            self._slab_pool = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        return self._slab_pool
+
     def slab_granularity(self):
         return int(self.lib.tomo_back_adjoint_slab_granularity())
 
@@ -260,13 +268,19 @@ class CudaBackend(object):
         self.d2h_bytes += 4 * out3.numel()
         return ret
 
-    def adjoint_host(self, y_host, out_host=None, chunk_views=None, to_host=True):
+    def sync_host(self):
+        """Wait until every copy queued by the ``*_host`` entry points has landed (for calls made with ``wait=False``)."""
+        self._copy_stream().synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def adjoint_host(self, y_host, out_host=None, chunk_views=None, to_host=True, wait=True):
         """vol = A^T y with HOST input and output: projection chunks go up on a side stream while the
         previous chunk is backprojected (accumulating launches), the volume comes down once.
         ``to_host=False`` returns the device volume instead (callers that all-reduce before the download): it is
         this backend's reusable staging buffer, valid until the next ``*_host`` call on the backend -- clone it to
         keep it.  Either way the call returns only after the uploads of ``y_host`` have completed, so the host
-        buffer may be reused at once."""
+        buffer may be reused at once.  ``wait=False`` queues the download of the volume on the copy stream and returns
+        without waiting for it (``out_host`` is valid after ``sync_host()``): the next operator's kernels overlap it."""
         y_host = self._host(y_host)
         if y_host.numel() != self.n_proj * self.n_det:
             raise ValueError("projections have %d elements, operator expects %d" % (y_host.numel(), self.n_proj * self.n_det))
@@ -297,9 +311,16 @@ class CudaBackend(object):
         if not to_host:
             cp.synchronize()                     # the pinned input may be reused by the caller from here on
             return vol_d
+        self.d2h_bytes += 4 * out_host.numel()
+        if not wait:
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(cp):
+                cp.wait_event(done)
+                out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
+            return out_host
         out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
         cur.synchronize()
-        self.d2h_bytes += 4 * out_host.numel()
         return out_host
 
     def proj_grad_host(self, vol_host, meas_host, chunk_views=None, vol_dev=None, to_host=True):
