@@ -167,11 +167,25 @@ TOMO_API int tomo_back_voxel_bilinear(const TomoGeom* geom, const void* views_de
  *   det_dev   [n_proj][ndz][ndx]      float32  (x FASTEST: the Fortran's det_img(fz, fx), transposed w.r.t. the
  *                                               ray-driven projections)
  *   grad_dev  [n_proj][6][ndz][ndx]   float32, nullable
- * Outputs are zeroed by the call.  This is a scatter: contributions are accumulated with float32 atomic adds,
- * so the summation ORDER (not the set of terms) varies between runs -- results agree to float32 rounding, not
- * bitwise.  vol_dev is the UNPADDED volume. */
+ * Outputs are zeroed by the call.  vol_dev is the UNPADDED volume.  The operator is a scatter:
+ *   tomo_voxel_splat                float32 atomic adds: the summation ORDER (not the set of terms) varies between runs, so
+ *                                   results agree to float32 rounding, not bitwise;
+ *   tomo_voxel_splat_deterministic  every contribution is added as a 64-bit fixed-point integer (scale from max |vol| and the
+ *                                   geometry, resolution ~1e-14 of the largest term) and converted at the end: integer addition
+ *                                   is associative, so results are bitwise reproducible and more accurate than float32
+ *                                   accumulation.  Needs tomo_voxel_splat_workspace_bytes() bytes of device workspace. */
 TOMO_API int tomo_voxel_splat(const TomoGeom* geom, const void* views_dev, int n_proj, const float* vol_dev,
                      float* det_dev, float* grad_dev, void* stream);
+TOMO_API size_t tomo_voxel_splat_workspace_bytes(const TomoGeom* geom, int n_proj, int with_grad);
+TOMO_API int tomo_voxel_splat_deterministic(const TomoGeom* geom, const void* views_dev, int n_proj, const float* vol_dev,
+                                   float* det_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* vol (+)= S^T det, the transpose of the splat matrix S that bilinear_sparse emits (src/vox_wt_grad.f90:58-112 through
+ * utilities/voxel_utilities.py:50-79: rows = detector pixels fx + ndim_x * fz, columns = voxels, float32 weights, taps
+ * bounds-checked one by one).  det_dev [n_proj][ndz][ndx] (x fastest, as tomo_voxel_splat writes it).  A per-voxel gather:
+ * no atomics, bitwise reproducible. */
+TOMO_API int tomo_voxel_splat_adjoint(const TomoGeom* geom, const void* views_dev, int n_proj, const float* det_dev,
+                             float* vol_dev, int accumulate, void* stream);
 
 /* Projection + 6-DOF rigid-body gradient for all views in one launch.  Replaces
  * ProjectionMatrix.projection_gradient (utilities/projection_operators.py:112-122) ->

@@ -417,3 +417,88 @@ void orc_voxel_splat_grad(long n_vox, const int32_t *floor_x, const int32_t *flo
         }
     }
 }
+
+/* COO emitter of the voxel-driven forward matrix: restates bilinear_sparse, src/vox_wt_grad.f90:58-112.
+ * floor_x / floor_z int32, alpha_x / alpha_z float32 (the Fortran's real(4) arguments), 4 taps per voxel, each
+ * bounds-checked on its own; det index = fx + ndim_x * fz (x fastest); weights are float32 products.
+ * dat/det/wts hold 4*n_vox entries, unused tail = -999; returns n_inds. */
+long orc_bilinear_sparse(long n_vox, const int32_t *floor_x, const int32_t *floor_z, const float *alpha_x,
+                         const float *alpha_z, long ndim_x, long ndim_z, int32_t *dat, int32_t *det, float *wts)
+{
+    for (long i = 0; i < 4 * n_vox; ++i) { dat[i] = -999; det[i] = -999; wts[i] = -999.0f; }
+    long k = 0;
+    for (long i = 0; i < n_vox; ++i) {
+        const long fx = floor_x[i], fz = floor_z[i];          /* 0-based */
+        const float ax = alpha_x[i], az = alpha_z[i];
+        if (IN(fx, ndim_x) && IN(fz, ndim_z))         { dat[k] = (int32_t)i; det[k] = (int32_t)(fx + ndim_x * fz);           wts[k] = (1.0f - ax) * (1.0f - az); ++k; }
+        if (IN(fx + 1, ndim_x) && IN(fz, ndim_z))     { dat[k] = (int32_t)i; det[k] = (int32_t)(fx + 1 + ndim_x * fz);       wts[k] = ax * (1.0f - az); ++k; }
+        if (IN(fx, ndim_x) && IN(fz + 1, ndim_z))     { dat[k] = (int32_t)i; det[k] = (int32_t)(fx + ndim_x * (fz + 1));     wts[k] = (1.0f - ax) * az; ++k; }
+        if (IN(fx + 1, ndim_x) && IN(fz + 1, ndim_z)) { dat[k] = (int32_t)i; det[k] = (int32_t)(fx + 1 + ndim_x * (fz + 1)); wts[k] = ax * az; ++k; }
+    }
+    return k;
+}
+
+/* ---- orphan matrix-free forward projector, float32 throughout ---------------------------------------------------
+ * Restates forward_project (src/forward_projection.f90:1-68) with rigid_transformation and ray_forward_trilinear
+ * (src/external_forward_projection.f90:1-28, 73-160) and the rotation matrices of src/rotations_module.f90 in C `float`
+ * arithmetic, operation for operation:
+ *   p = Rz(phi) Rx(alpha) (Ry(beta) x + t) - origin  for the source and the detector points (f90:31-37)
+ *   r_hat, r_length from RAY 1 ONLY (:41-43);  n_on_ray = NINT(r_length / step_size) (:44 -- the live path truncates)
+ *   point j (1-based) = p0 + (j-1)*step_size*r_hat (:52-56);  the cor_shift ARGUMENT IS NEVER READ (:1,10 vs body)
+ *   trilinear sum with per-corner bounds checks, w_floor = 1 - (p - real(floor(p))) (external:90-91)
+ * source / detector (3, n_rays) C-order float32, xyz (n_proj, 3), ax (n_proj, n_rays) C-order. */
+static void rotf(int axis, float a, float m[3][3])
+{
+    const float c = cosf(a), s = sinf(a);
+    if (axis == 2)      { const float t[3][3] = {{c, -s, 0.f}, {s, c, 0.f}, {0.f, 0.f, 1.f}}; memcpy(m, t, sizeof(t)); }
+    else if (axis == 0) { const float t[3][3] = {{1.f, 0.f, 0.f}, {0.f, c, -s}, {0.f, s, c}}; memcpy(m, t, sizeof(t)); }
+    else                { const float t[3][3] = {{c, 0.f, s}, {0.f, 1.f, 0.f}, {-s, 0.f, c}}; memcpy(m, t, sizeof(t)); }
+}
+
+void orc_forward_project_orphan_f32(const float *alpha, const float *beta, const float *phi, const float *xyz,
+                                    long n_proj, const float *source, const float *detector, long n_rays,
+                                    const float *origin, float step_size, long nx, long ny, long nz,
+                                    const float *recon, float *ax)
+{
+    for (long np = 0; np < n_proj; ++np) {
+        float rz[3][3], rx[3][3], ry[3][3], rzx[3][3];
+        rotf(2, phi[np], rz); rotf(0, alpha[np], rx); rotf(1, beta[np], ry);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+            rzx[i][j] = rz[i][0] * rx[0][j] + rz[i][1] * rx[1][j] + rz[i][2] * rx[2][j];
+        const float *t = xyz + 3 * np;
+        float rhat[3] = {0.f, 0.f, 0.f}, rlen = 0.f;
+        long n_on_ray = 0;
+        for (long r = 0; r < n_rays; ++r) {
+            float p0[3], p1[3];
+            for (int which = 0; which < 2; ++which) {
+                const float *src = which ? detector : source;
+                float x[3] = {src[r], src[n_rays + r], src[2 * n_rays + r]}, y[3], *out = which ? p1 : p0;
+                for (int i = 0; i < 3; ++i) y[i] = (ry[i][0] * x[0] + ry[i][1] * x[1] + ry[i][2] * x[2]) + t[i];
+                for (int i = 0; i < 3; ++i) out[i] = (rzx[i][0] * y[0] + rzx[i][1] * y[1] + rzx[i][2] * y[2]) - origin[i];
+            }
+            if (r == 0) {                                   /* direction and sample count from the first ray only */
+                const float d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+                rlen = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                for (int i = 0; i < 3; ++i) rhat[i] = d[i] / rlen;
+                n_on_ray = lroundf(rlen / step_size);        /* NINT */
+            }
+            float acc = 0.f;
+            for (long j = 0; j < n_on_ray; ++j) {
+                float p[3], wf[3];
+                long f[3];
+                for (int i = 0; i < 3; ++i) {
+                    p[i] = p0[i] + ((float)j * step_size) * rhat[i];
+                    const float fl = floorf(p[i]);
+                    f[i] = (long)fl;
+                    wf[i] = 1.0f - (p[i] - fl);
+                }
+                const long X[2] = {f[0], f[0] + 1}, Y[2] = {f[1], f[1] + 1}, Z[2] = {f[2], f[2] + 1};
+                const float WX[2] = {wf[0], 1.0f - wf[0]}, WY[2] = {wf[1], 1.0f - wf[1]}, WZ[2] = {wf[2], 1.0f - wf[2]};
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c)   /* fff ffc fcf fcc cff ... */
+                    if (IN(X[a], nx) && IN(Y[b], ny) && IN(Z[c], nz))
+                        acc = acc + recon[(X[a] * ny + Y[b]) * nz + Z[c]] * (WX[a] * WY[b] * WZ[c]);
+            }
+            ax[np * n_rays + r] = acc;
+        }
+    }
+}

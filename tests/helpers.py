@@ -65,7 +65,9 @@ class _HostBackendBase(object):
 
     def set_poses(self, poses):
         poses = np.asarray(poses, dtype=np.float64)
-        self.poses = np.ascontiguousarray(poses.reshape(-1, poses.shape[-1])[:, :9])
+        poses = poses.reshape(-1, poses.shape[-1])
+        self.poses12 = np.ascontiguousarray(poses) if poses.shape[1] == 12 else None     # caller-chosen sample counts
+        self.poses = np.ascontiguousarray(poses[:, :9])
         self.n_proj = self.poses.shape[0]
         self._bound_state = None
 
@@ -119,7 +121,7 @@ class EmuBackend(_HostBackendBase):
     def set_poses(self, poses):
         super().set_poses(poses)
         self.views = np.zeros((self.n_proj, _lib.VIEW_STRIDE))
-        full = full_pose_table(self.geometry, self.poses)
+        full = self.poses12 if self.poses12 is not None else full_pose_table(self.geometry, self.poses)
         rc = self.L.tomo_views_compute_host(ctypes.byref(self.cg), _P(full), self.n_proj, _P(self.views))
         _lib.check(rc, "tomo_views_compute_host")
 

@@ -161,3 +161,22 @@ def test_adjoint_pair_at_64cubed():
     lhs = np.vdot(be.forward(x).numpy().astype(np.float64).ravel(), y.astype(np.float64).ravel())
     rhs = np.vdot(x.astype(np.float64).ravel(), be.adjoint(y).numpy().astype(np.float64).ravel())
     assert abs(lhs - rhs) <= 1e-6 * abs(rhs)
+
+
+def test_orphan_forward_project_variant():
+    """ProjectionMatrix.forward_project = the orphan forward_project (src/forward_projection.f90): NINT sample count, cor_shift
+    ignored -- against the float32 restatement of the Fortran (oracle.forward_project_orphan), on a volume WIDER than deep so
+    that the extra trailing sample the NINT rule adds does touch voxels (the live path would drop it for some views)."""
+    from tomography_alignment_b200 import ProjectionMatrix
+    shape, dshape, n_proj = (30, 8, 12), (30, 12), 5
+    g, og = make_geoms(shape, dshape, n_proj, cor=[0.6, 0.0, 0.0])           # the orphan ignores this shift
+    phi, alpha, beta, xyz = random_poses(n_proj, 12, tilt=0.03, shift=1.0, phis=[0.1, 0.9, 1.5, 2.2, 3.0])
+    rec = np.random.default_rng(7).random(shape).astype(np.float32)
+    pm = ProjectionMatrix(g, backend=EmuBackend(g))
+    ax = pm.forward_project(rec, alpha, beta, phi, xyz, cor_shift=g.cor_shift)
+    ref = O.forward_project_orphan(og, rec, alpha, beta, phi, xyz)
+    assert ax.shape == (n_proj, g.n_det) and ax.dtype == np.float32
+    assert rel_l2(ax, ref) <= TOL_PROJ
+    # and it is NOT the live operator here: the live path applies cor_shift (and may march one sample fewer)
+    live = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz).forward(rec)
+    assert rel_l2(ax, live) > 1e-3

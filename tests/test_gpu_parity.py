@@ -617,3 +617,66 @@ def test_view_kinds_skip_launches_without_changing_results():
         assert be.launches - n0 > launched
         be.kinds = kinds
         assert torch.equal(f, f0) and torch.equal(b, b0) and torch.equal(gr["grad6"], gr0["grad6"]) and torch.equal(gr["dproj"], gr0["dproj"])
+
+
+@pytest.mark.parametrize("shape,dshape,kw", [((12, 10, 14), (12, 14), dict()), ((16, 16, 16), (20, 12), dict(tilt=0.1, shift=3.0)),
+                                              ((10, 10, 10), (10, 10), dict(cor=[0.4, 0.0, -0.3]))])
+def test_voxel_splat_deterministic_and_transpose(shape, dshape, kw):
+    """tomo_voxel_splat_deterministic (64-bit fixed-point accumulation) against the restated bilinear_vox_interp, bitwise
+    repeatable; tomo_voxel_splat_adjoint against the transposed COO matrix of bilinear_sparse (src/vox_wt_grad.f90:58-112);
+    <S x, y> = <x, S^T y>."""
+    n_proj = 3
+    g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)
+    rec = np.random.default_rng(5).random(shape).astype(np.float32)
+    det, grad = be.voxel_splat(torch.as_tensor(rec), deterministic=True)
+    y = np.random.default_rng(6).random((n_proj, dshape[1], dshape[0])).astype(np.float32)       # [view][z'][x']
+    st_ref = np.zeros(og.n_vox)
+    for i in range(n_proj):
+        d_ref, g_ref = O.voxel_forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], rec)
+        assert rel_l2(det[i].cpu().numpy(), d_ref) <= 1e-6          # float32 output of an exact sum of float32 terms
+        assert rel_l2(grad[i].cpu().numpy(), g_ref) <= TOL_GRAD
+        dat, di, w = O.voxel_forward_sparse(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i])
+        S = sparse.coo_matrix((w.astype(np.float64), (di, dat)), shape=(og.n_det, og.n_vox)).tocsr()
+        st_ref += S.T @ y[i].ravel().astype(np.float64)
+    for _ in range(2):
+        d2, g2 = be.voxel_splat(torch.as_tensor(rec), deterministic=True)
+        assert torch.equal(d2, det) and torch.equal(g2, grad)
+    d_only, none = be.voxel_splat(torch.as_tensor(rec), want_grad=False, deterministic=True)
+    assert none is None and torch.equal(d_only, det)
+    st = be.voxel_splat_adjoint(torch.as_tensor(y))
+    assert rel_l2(st.cpu().numpy(), st_ref) <= TOL_PROJ
+    lhs = float((det.double().cpu() * torch.as_tensor(y).double()).sum())
+    rhs = float((st.double().cpu().ravel() * torch.as_tensor(rec).double().ravel()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(rhs)
+
+
+def test_voxel_splat_at_256_cubed_many_views():
+    """The splat's view index lives in grid.x (r1 capped ny/4 * n_proj at 65535: TOMO_E_RANGE at 512^3 x 720): 256^3 x 1100
+    views = 70400 (y block, view) pairs; one seeded view of the result against the oracle, the deterministic variant bitwise
+    repeatable and within float32 rounding of the atomic one."""
+    n, n_proj = 256, 1100
+    g, og = make_geoms((n, n, n), (n, n), n_proj)
+    phi, alpha, beta, xyz = benchmark_poses(n_proj)
+    be = cuda_backend(g)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    rec = torch.rand((n, n, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    det, _ = be.voxel_splat(rec, want_grad=False)
+    det_fx, _ = be.voxel_splat(rec, want_grad=False, deterministic=True)
+    i = 777
+    d_ref, _ = O.voxel_forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], rec.cpu().numpy())
+    assert rel_l2(det[i].cpu().numpy(), d_ref) <= TOL_PROJ and rel_l2(det_fx[i].cpu().numpy(), d_ref) <= 1e-6
+    assert rel_l2(det.cpu().numpy(), det_fx.cpu().numpy()) <= 1e-6
+    d2, _ = be.voxel_splat(rec, want_grad=False, deterministic=True)
+    assert torch.equal(d2, det_fx)
+
+
+def test_orphan_forward_project_on_gpu():
+    """ProjectionMatrix.forward_project (orphan semantics: NINT sample count, cor_shift ignored) against the float32
+    restatement of src/forward_projection.f90."""
+    shape, dshape, n_proj = (30, 8, 12), (30, 12), 5
+    g, og = make_geoms(shape, dshape, n_proj, cor=[0.6, 0.0, 0.0])
+    phi, alpha, beta, xyz = random_poses(n_proj, 12, tilt=0.03, shift=1.0, phis=[0.1, 0.9, 1.5, 2.2, 3.0])
+    rec = np.random.default_rng(7).random(shape).astype(np.float32)
+    pm = ProjectionMatrix(g, device="cuda:0")
+    ax = pm.forward_project(rec, alpha, beta, phi, xyz, cor_shift=g.cor_shift)
+    assert ax.shape == (n_proj, g.n_det) and rel_l2(ax, O.forward_project_orphan(og, rec, alpha, beta, phi, xyz)) <= TOL_PROJ

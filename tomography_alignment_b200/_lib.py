@@ -80,6 +80,12 @@ def load():
     L.tomo_back_voxel_bilinear.argtypes = [G, vp, ci, vp, vp, vp, ci, vp]
     L.tomo_voxel_splat.restype = ci
     L.tomo_voxel_splat.argtypes = [G, vp, ci, vp, vp, vp, vp]
+    L.tomo_voxel_splat_workspace_bytes.restype = sz
+    L.tomo_voxel_splat_workspace_bytes.argtypes = [G, ci, ci]
+    L.tomo_voxel_splat_deterministic.restype = ci
+    L.tomo_voxel_splat_deterministic.argtypes = [G, vp, ci, vp, vp, vp, vp, sz, vp]
+    L.tomo_voxel_splat_adjoint.restype = ci
+    L.tomo_voxel_splat_adjoint.argtypes = [G, vp, ci, vp, vp, ci, vp]
     L.tomo_tv_dual_error.restype = ci
     L.tomo_tv_dual_error.argtypes = [ci, ci, ci, ctypes.c_float, vp, vp, vp, vp]
     L.tomo_tv_dual_update.restype = ci

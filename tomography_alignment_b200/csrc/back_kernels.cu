@@ -43,6 +43,7 @@
 // contiguous in the projections, so both sides are coalesced.
 #include <cuda.h>            // CUtensorMap types; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
 #include <cuda_runtime.h>
+#include <cmath>
 #include "tomo_common.h"
 #include "back_core.h"
 
@@ -517,14 +518,50 @@ adjoint_tile_kernel(const BackArgs A, const int ntx, const int nty, const int nt
     }
 }
 
-// Voxel-driven forward splat + gradient image (src/vox_wt_grad.f90:1-55).  One thread per (voxel, view);
-// lanes along z.  Scatter with float32 atomic adds (see include/tomo_b200.h for the determinism note).
-__global__ void __launch_bounds__(BZ * BY * BX)
-voxel_splat_kernel(const BackArgs A, const float* __restrict__ vol, float* __restrict__ det, float* __restrict__ grad)
+// Voxel-driven forward splat + gradient image (src/vox_wt_grad.f90:1-55).  One thread per (voxel, view); lanes along z.
+// A scatter: FIXED = false adds float32 contributions with atomicAdd (summation order varies between runs); FIXED = true
+// adds them as 64-bit fixed-point integers (atomicAdd on unsigned long long: integer addition is associative, so the sums
+// are bitwise reproducible) that splat_fixed_finalize_kernel converts back.  blockIdx.x = view * nzb + z block, so the view
+// count is not limited by the 65535 cap of grid.y.
+struct SplatFixed {
+    unsigned long long* det;      // [n_proj][n_det]
+    unsigned long long* grad;     // [n_proj][6][n_det], nullable
+    const unsigned* maxabs;       // float bits of max |vol| (splat_maxabs_kernel)
+    double terms;                 // bound on the number of contributions one detector pixel can receive
+    double ext;                   // bound on |voxel centre coordinate| summed over the axes (for the derivative magnitudes)
+};
+
+// scale of the fixed-point sums: |contribution| <= m, at most `terms` of them per pixel -> |sum| * scale <= 2^62
+__device__ __forceinline__ double splat_scale(double m, double terms)
 {
-    const int z = blockIdx.x * BZ + threadIdx.x;
-    const int yb = blockIdx.y % ((A.ny + BY - 1) / BY), view = blockIdx.y / ((A.ny + BY - 1) / BY);
-    const int y = yb * BY + threadIdx.y;
+    return (m > 0.0) ? 4611686018427387904.0 / (m * terms) : 1.0;
+}
+// bound on |g0|, |g2| of a view (rows of derivative_rigid, voxel_utilities.py:23-48: rotation rows applied to a centre / to t)
+__device__ __forceinline__ double splat_gmax(const double* __restrict__ V, double ext)
+{
+    return 2.0 * (ext + fabs(V[V_VTR + 0]) + fabs(V[V_VTR + 1]) + fabs(V[V_VTR + 2])) + 2.0;
+}
+
+__global__ void splat_maxabs_kernel(const float* __restrict__ vol, size_t n, unsigned* __restrict__ out)
+{
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(vol[i]);
+        m = (a > m && a < 3.0e38f) ? a : m;               // Inf / NaN voxels do not set the scale
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));          // non-negative floats order like their bits
+}
+
+template <bool FIXED>
+__global__ void __launch_bounds__(BZ * BY * BX)
+voxel_splat_kernel(const BackArgs A, const float* __restrict__ vol, float* __restrict__ det, float* __restrict__ grad,
+                   const SplatFixed F, int nzb)
+{
+    const int view = blockIdx.x / nzb;
+    const int z = (blockIdx.x % nzb) * BZ + threadIdx.x;
+    const int y = blockIdx.y * BY + threadIdx.y;
     const int x = blockIdx.z * BX + threadIdx.z;
     if (x >= A.nx || y >= A.ny || z >= A.nz) return;
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
@@ -536,8 +573,9 @@ voxel_splat_kernel(const BackArgs A, const float* __restrict__ vol, float* __res
     const float ax = (float)(ux - flx), az = (float)(uz - flz);       // alpha_x, alpha_z are float32 in the reference
     const int fx = (int)fmin(fmax(flx, -2.0), 1.0e9), fz = (int)fmin(fmax(flz, -2.0), 1.0e9);
     const size_t n_det = (size_t)A.ndx * A.ndz;
+    const bool want_grad = FIXED ? (F.grad != nullptr) : (grad != nullptr);
     float g0[6], g2[6];
-    if (grad) {
+    if (want_grad) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const double* q0 = V + V_SPL + (k * 2 + 0) * 4;
@@ -545,6 +583,12 @@ voxel_splat_kernel(const BackArgs A, const float* __restrict__ vol, float* __res
             g0[k] = (float)(q0[0] * cx + q0[1] * cy + q0[2] * cz + q0[3]);
             g2[k] = (float)(q2[0] * cx + q2[1] * cy + q2[2] * cz + q2[3]);
         }
+    }
+    double sc = 0.0, scg = 0.0;
+    if (FIXED) {
+        const double m = (double)__uint_as_float(*F.maxabs);
+        sc = splat_scale(m, F.terms);
+        scg = splat_scale(m * splat_gmax(V, F.ext), F.terms);
     }
     // taps (fx,fz), (fx+1,fz), (fx,fz+1), (fx+1,fz+1): weights and d/dx', d/dz' factors of vox_wt_grad.f90:25-50
     const int   tx[4] = {fx, fx + 1, fx, fx + 1}, tzz[4] = {fz, fz, fz + 1, fz + 1};
@@ -555,13 +599,68 @@ voxel_splat_kernel(const BackArgs A, const float* __restrict__ vol, float* __res
     for (int t = 0; t < 4; ++t) {
         if (tx[t] < 0 || tx[t] >= A.ndx || tzz[t] < 0 || tzz[t] >= A.ndz) continue;
         const size_t di = (size_t)tzz[t] * A.ndx + tx[t];
-        atomicAdd(det + (size_t)view * n_det + di, rec * w[t]);
-        if (grad) {
+        const float c = rec * w[t];
+        if (FIXED) atomicAdd(F.det + (size_t)view * n_det + di, (unsigned long long)__double2ll_rn((double)c * sc));
+        else       atomicAdd(det + (size_t)view * n_det + di, c);
+        if (want_grad) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                atomicAdd(grad + ((size_t)view * 6 + k) * n_det + di, g0[k] * G0[t] * rec + g2[k] * G2[t] * rec);
+            for (int k = 0; k < 6; ++k) {
+                const float cg = g0[k] * G0[t] * rec + g2[k] * G2[t] * rec;
+                if (FIXED) atomicAdd(F.grad + ((size_t)view * 6 + k) * n_det + di, (unsigned long long)__double2ll_rn((double)cg * scg));
+                else       atomicAdd(grad + ((size_t)view * 6 + k) * n_det + di, cg);
+            }
         }
     }
+}
+
+__global__ void splat_fixed_finalize_kernel(const BackArgs A, const SplatFixed F, float* __restrict__ det, float* __restrict__ grad)
+{
+    const size_t n_det = (size_t)A.ndx * A.ndz, n_img = (size_t)A.n_proj * (F.grad ? 7 : 1);
+    const double m = (double)__uint_as_float(*F.maxabs);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_img * n_det; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / n_det, px = i % n_det;
+        if (img < (size_t)A.n_proj) {
+            det[img * n_det + px] = (float)((double)(long long)F.det[img * n_det + px] / splat_scale(m, F.terms));
+        } else {
+            const size_t gi = img - A.n_proj, view = gi / 6;
+            const double scg = splat_scale(m * splat_gmax(A.views + view * TOMO_VIEW_STRIDE, F.ext), F.terms);
+            grad[gi * n_det + px] = (float)((double)(long long)F.grad[gi * n_det + px] / scg);
+        }
+    }
+}
+
+// Transpose of the splat: vol[v] (+)= sum_views sum_taps w(v, tap) * det[view][tap] with the splat's own weights (the matrix
+// bilinear_sparse emits, src/vox_wt_grad.f90:58-112, applied transposed).  A gather: one thread per voxel, no atomics.
+__global__ void __launch_bounds__(BZ * BY * BX)
+voxel_splat_adjoint_kernel(const BackArgs A)
+{
+    const int z = blockIdx.x * BZ + threadIdx.x;
+    const int y = blockIdx.y * BY + threadIdx.y;
+    const int x = blockIdx.z * BX + threadIdx.z;
+    if (x >= A.nx || y >= A.ny || z >= A.nz) return;
+    const size_t n_det = (size_t)A.ndx * A.ndz;
+    const double cx = A.vox0[0] + x * A.vpix[0], cy = A.vox0[1] + y * A.vpix[1], cz = A.vox0[2] + z * A.vpix[2];
+    float acc = 0.f;
+    for (int view = 0; view < A.n_proj; ++view) {
+        const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+        const float* __restrict__ P = A.proj + (size_t)view * n_det;              // [ndz][ndx], x fastest
+        const double ux = V[V_VROT + 0] * cx + V[V_VROT + 1] * cy + V[V_VROT + 2] * cz + V[V_VTR + 0] - V[V_SORG + 0];
+        const double uz = V[V_VROT + 6] * cx + V[V_VROT + 7] * cy + V[V_VROT + 8] * cz + V[V_VTR + 2] - V[V_SORG + 1];
+        const double flx = floor(ux), flz = floor(uz);
+        const float ax = (float)(ux - flx), az = (float)(uz - flz);
+        const int fx = (int)fmin(fmax(flx, -2.0), 1.0e9), fz = (int)fmin(fmax(flz, -2.0), 1.0e9);
+        const bool x0 = (fx >= 0 && fx < A.ndx), x1 = (fx + 1 >= 0 && fx + 1 < A.ndx);
+        const bool z0 = (fz >= 0 && fz < A.ndz), z1 = (fz + 1 >= 0 && fz + 1 < A.ndz);
+        const float* __restrict__ c = P + (ptrdiff_t)fz * A.ndx + fx;
+        float v = 0.f;
+        if (x0 && z0) v = fmaf(__ldg(c), (1.f - ax) * (1.f - az), v);
+        if (x1 && z0) v = fmaf(__ldg(c + 1), ax * (1.f - az), v);
+        if (x0 && z1) v = fmaf(__ldg(c + A.ndx), (1.f - ax) * az, v);
+        if (x1 && z1) v = fmaf(__ldg(c + A.ndx + 1), ax * az, v);
+        acc += v;
+    }
+    const size_t vi = ((size_t)x * A.ny + y) * A.nz + z;
+    A.vol[vi] = A.accumulate ? A.vol[vi] + acc : acc;
 }
 
 }  // namespace
@@ -725,19 +824,73 @@ extern "C" int tomo_back_voxel_bilinear(const TomoGeom* g, const void* views, in
     return tomo_check_cuda(cudaGetLastError(), "voxel_bilinear_kernel");
 }
 
-extern "C" int tomo_voxel_splat(const TomoGeom* g, const void* views, int n_proj, const float* vol,
-                                float* det, float* grad, void* stream)
+static int splat_launch(const TomoGeom* g, const void* views, int n_proj, const float* vol, float* det, float* grad,
+                        void* workspace, size_t workspace_bytes, bool fixed, void* stream)
 {
     BackArgs A; dim3 grid;
     if (!det) { tomo_set_error("tomo_voxel_splat: det_dev is NULL"); return TOMO_E_ARG; }
     if (int e = fill_back(g, views, n_proj, vol, det, 0, &A, &grid)) return e;
-    const size_t n_det = (size_t)g->ndx * g->ndz;
-    cudaError_t ce = cudaMemsetAsync(det, 0, sizeof(float) * n_det * n_proj, (cudaStream_t)stream);
-    if (ce == cudaSuccess && grad) ce = cudaMemsetAsync(grad, 0, sizeof(float) * 6 * n_det * n_proj, (cudaStream_t)stream);
-    if (int e = tomo_check_cuda(ce, "tomo_voxel_splat: cudaMemsetAsync")) return e;
-    const unsigned nyb = (g->ny + BY - 1) / BY;
-    if ((double)nyb * n_proj > 65535.0) { tomo_set_error("tomo_voxel_splat: ny/4 * n_proj exceeds the launch grid"); return TOMO_E_RANGE; }
-    grid.y = nyb * n_proj;
-    voxel_splat_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A, vol, det, grad);
-    return tomo_check_cuda(cudaGetLastError(), "voxel_splat_kernel");
+    const size_t n_det = (size_t)g->ndx * g->ndz, n_vox = (size_t)g->nx * g->ny * g->nz;
+    const int nzb = (g->nz + BZ - 1) / BZ;
+    if ((double)nzb * n_proj >= 2147483647.0) { tomo_set_error("tomo_voxel_splat: too many blocks for one launch"); return TOMO_E_RANGE; }
+    grid.x = (unsigned)(nzb * n_proj);
+    cudaStream_t st = (cudaStream_t)stream;
+    SplatFixed F = {nullptr, nullptr, nullptr, 0.0, 0.0};
+    if (!fixed) {
+        cudaError_t ce = cudaMemsetAsync(det, 0, sizeof(float) * n_det * n_proj, st);
+        if (ce == cudaSuccess && grad) ce = cudaMemsetAsync(grad, 0, sizeof(float) * 6 * n_det * n_proj, st);
+        if (int e = tomo_check_cuda(ce, "tomo_voxel_splat: cudaMemsetAsync")) return e;
+        voxel_splat_kernel<false><<<grid, dim3(BZ, BY, BX), 0, st>>>(A, vol, det, grad, F, nzb);
+        return tomo_check_cuda(cudaGetLastError(), "voxel_splat_kernel");
+    }
+    const size_t need = tomo_voxel_splat_workspace_bytes(g, n_proj, grad != nullptr);
+    if (!workspace || workspace_bytes < need) {
+        tomo_set_error("tomo_voxel_splat_deterministic: workspace too small (see tomo_voxel_splat_workspace_bytes)");
+        return TOMO_E_WORKSPACE;
+    }
+    cudaError_t ce = cudaMemsetAsync(workspace, 0, need, st);
+    if (int e = tomo_check_cuda(ce, "tomo_voxel_splat_deterministic: cudaMemsetAsync")) return e;
+    unsigned* maxabs = (unsigned*)workspace;                             // 16 bytes reserved, then the integer images
+    F.det = (unsigned long long*)((char*)workspace + 16);
+    F.grad = grad ? F.det + n_det * n_proj : nullptr;
+    F.maxabs = maxabs;
+    // a detector pixel collects the voxels of a tube of cross-section <= 2 x 2 pixels through the volume, 4 taps each
+    F.terms = 16.0 * ((double)g->nx + g->ny + g->nz) + 16.0;
+    F.ext = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        const double n = (a == 0) ? g->nx : (a == 1) ? g->ny : g->nz;
+        const double lo = std::fabs(g->vox_origin[a]), hi = std::fabs(g->vox_origin[a] + (n - 1.0) * g->vox_pix[a]);
+        F.ext += lo > hi ? lo : hi;
+    }
+    splat_maxabs_kernel<<<148 * 4, 256, 0, st>>>(vol, n_vox, maxabs);
+    voxel_splat_kernel<true><<<grid, dim3(BZ, BY, BX), 0, st>>>(A, vol, nullptr, nullptr, F, nzb);
+    splat_fixed_finalize_kernel<<<148 * 8, 256, 0, st>>>(A, F, det, grad);
+    return tomo_check_cuda(cudaGetLastError(), "voxel_splat_kernel<fixed>");
+}
+
+extern "C" size_t tomo_voxel_splat_workspace_bytes(const TomoGeom* g, int n_proj, int with_grad)
+{
+    if (!g || n_proj <= 0) return 0;
+    return 16 + sizeof(unsigned long long) * (size_t)g->ndx * g->ndz * (size_t)n_proj * (with_grad ? 7 : 1);
+}
+
+extern "C" int tomo_voxel_splat(const TomoGeom* g, const void* views, int n_proj, const float* vol,
+                                float* det, float* grad, void* stream)
+{
+    return splat_launch(g, views, n_proj, vol, det, grad, nullptr, 0, false, stream);
+}
+
+extern "C" int tomo_voxel_splat_deterministic(const TomoGeom* g, const void* views, int n_proj, const float* vol,
+                                              float* det, float* grad, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return splat_launch(g, views, n_proj, vol, det, grad, workspace, workspace_bytes, true, stream);
+}
+
+extern "C" int tomo_voxel_splat_adjoint(const TomoGeom* g, const void* views, int n_proj, const float* det,
+                                        float* vol, int accumulate, void* stream)
+{
+    BackArgs A; dim3 grid;
+    if (int e = fill_back(g, views, n_proj, det, vol, accumulate, &A, &grid)) return e;
+    voxel_splat_adjoint_kernel<<<grid, dim3(BZ, BY, BX), 0, (cudaStream_t)stream>>>(A);
+    return tomo_check_cuda(cudaGetLastError(), "voxel_splat_adjoint_kernel");
 }

@@ -393,19 +393,42 @@ class CudaBackend(object):
         self.launches += 1
         return out
 
-    def voxel_splat(self, vol, want_grad=True):
+    def voxel_splat(self, vol, want_grad=True, deterministic=False):
         """Orphan voxel-driven forward splat (+ gradient image), src/vox_wt_grad.f90:1-55: returns
-        (det (n_proj, ndz, ndx), grad (n_proj, 6, ndz, ndx) or None), x fastest."""
+        (det (n_proj, ndz, ndx), grad (n_proj, 6, ndz, ndx) or None), x fastest.  ``deterministic=True`` accumulates in
+        64-bit fixed point (tomo_voxel_splat_deterministic): bitwise reproducible, at the price of an integer workspace."""
         vol = self._as_vol(vol)
         ndx, ndz = self.det_shape
         det = torch.empty((self.n_proj, ndz, ndx), dtype=torch.float32, device=self.device)
         grad = torch.empty((self.n_proj, 6, ndz, ndx), dtype=torch.float32, device=self.device) if want_grad else None
         with torch.cuda.device(self.device):
-            rc = self.lib.tomo_voxel_splat(self._g(), _ptr(self.views), self.n_proj, _ptr(vol), _ptr(det), _ptr(grad),
-                                           self._stream())
+            if deterministic:
+                nbytes = self.lib.tomo_voxel_splat_workspace_bytes(self._g(), self.n_proj, int(bool(want_grad)))
+                ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=self.device)
+                rc = self.lib.tomo_voxel_splat_deterministic(self._g(), _ptr(self.views), self.n_proj, _ptr(vol), _ptr(det),
+                                                             _ptr(grad), _ptr(ws), nbytes, self._stream())
+                self.launches += 2
+            else:
+                rc = self.lib.tomo_voxel_splat(self._g(), _ptr(self.views), self.n_proj, _ptr(vol), _ptr(det), _ptr(grad),
+                                               self._stream())
         _lib.check(rc, "tomo_voxel_splat")
         self.launches += 1
         return det, grad
+
+    def voxel_splat_adjoint(self, det, out=None, accumulate=False):
+        """vol (+)= S^T det for the splat matrix S of bilinear_sparse (src/vox_wt_grad.f90:58-112); det (n_proj, ndz, ndx)."""
+        det = self._as_proj(det)
+        if out is None:
+            out = torch.empty(self.vol_shape, dtype=torch.float32, device=self.device)
+            accumulate = False
+        else:
+            self._check_out(out, self.vol_shape, "voxel_splat_adjoint")
+        with torch.cuda.device(self.device):
+            rc = self.lib.tomo_voxel_splat_adjoint(self._g(), _ptr(self.views), self.n_proj, _ptr(det), _ptr(out),
+                                                   int(bool(accumulate)), self._stream())
+        _lib.check(rc, "tomo_voxel_splat_adjoint")
+        self.launches += 1
+        return out
 
     def proj_grad(self, vol, meas=None, want_proj=True, want_dproj=True, want_grad6=None, repad=True):
         """Projection + 6-DOF gradient for all current views (tomo_proj_grad).

@@ -259,6 +259,18 @@ class ProjectionMatrix(object):
             self._backend = CudaBackend(self.geometry, self._device)
         return self._backend
 
+    def _aux_backend(self):
+        """Backend of the single-call entry points (projection_gradient, forward_project, ...): a CudaBackend of its own, so
+        that these calls do not disturb the view table of the operators projection_matrix() returned; an injected test
+        backend (tests exercising the host logic without a GPU) is shared."""
+        if self._grad_backend is None:
+            if self._backend is not None and type(self._backend).__name__ != "CudaBackend":
+                self._grad_backend = self._backend
+            else:
+                from .cuda_backend import CudaBackend
+                self._grad_backend = CudaBackend(self.geometry, self._device)
+        return self._grad_backend
+
     def projection_matrix(self, alpha=None, beta=None, phi=None, xyz_shift=None, voxel_mask=None):
         self.n_proj, self.angles, self.xyz_shift = normalise_poses(self.geometry, alpha, beta, phi, xyz_shift)
         self.voxel_mask = voxel_mask
@@ -291,14 +303,33 @@ class ProjectionMatrix(object):
         return (proj.cpu().numpy().astype(self.precision, copy=False),
                 grad.cpu().numpy().astype(self.precision, copy=False))
 
+    def forward_project(self, rec, alpha, beta, phi, xyz_shift, cor_shift=None):
+        """The orphan matrix-free forward projector ``forward_project`` (src/forward_projection.f90:1-68), all views at once,
+        with ITS semantics where they differ from the live path: the number of samples per ray is NINT(r_length / step_size)
+        (:44; the live path truncates, ray_voxel_utilities.py:88) and ``cor_shift`` is accepted but never applied (:1,10 --
+        the argument is ignored here as well).  Returns ax (n_proj, n_det) like the Fortran's ``ax(n_proj, n_rays)``.
+        Arithmetic is the float64-setup / float32-interpolation of tomo_forward, i.e. at least as accurate as the
+        all-float32 Fortran."""
+        n_proj, angles, xyz = normalise_poses(self.geometry, alpha, beta, phi, xyz_shift)
+        poses = np.zeros((n_proj, 12), dtype=np.float64)
+        poses[:, 0:3] = angles
+        poses[:, 3:6] = np.asarray(xyz, dtype=np.float64).reshape(n_proj, 3)
+        g = self.geometry
+        r_length = float(g._y_det) - float(g._y_source)          # |R (d - s)| = 2 sy for every pose
+        poses[:, 9] = float(np.rint(r_length / float(g.step_size)))
+        poses[:, 10] = r_length
+        be = self._aux_backend()
+        be.set_poses(poses)
+        was_torch = _is_torch(rec)
+        ax = be.forward(be._as_vol(rec if was_torch else np.ascontiguousarray(np.asarray(rec), dtype=np.float32)))
+        ax = ax.reshape(n_proj, -1)
+        return ax if was_torch else ax.cpu().numpy().astype(self.precision, copy=False)
+
     def voxel_projection_gradient(self, rec, alpha, beta, phi, xyz_shift, cor_shift):
         """The voxel-driven twin the reference keeps next to the ray-driven path
         (utilities/voxel_utilities.py:82-108, imported as vox_forward_proj_grad in projection_operators.py:8 but
         never called): (det_img.ravel() with x fastest, gradient (6, n_det)), rows [sx, sy, sz, theta, alpha, beta]."""
-        if self._grad_backend is None:
-            from .cuda_backend import CudaBackend
-            self._grad_backend = self._backend if (self._backend is not None and not hasattr(self._backend, "views")) \
-                else CudaBackend(self.geometry, self._device)
+        self._aux_backend()
         cor = np.asarray(cor_shift, dtype=np.float64).reshape(-1)[:3].reshape(1, 3)
         self._grad_backend.set_poses(pose_table(np.array([[phi, alpha, beta]], dtype=np.float64),
                                                 np.asarray(xyz_shift, dtype=np.float64).reshape(1, 3), cor))
@@ -314,12 +345,7 @@ class ProjectionMatrix(object):
         examples/align_rigid.py:40-49).  angles (n, 3) = [phi, alpha, beta].  With ``meas`` also
         returns grad6 (n, 6) = sum_rays (-dproj) * (meas - proj) and cost (n,) = 0.5*||meas - proj||^2,
         i.e. gradient_* / cost_* of utilities/alignment_functions.py before parameter masking."""
-        if self._grad_backend is None:
-            if self._backend is not None and not hasattr(self._backend, "views"):
-                self._grad_backend = self._backend          # injected test backend
-            else:
-                from .cuda_backend import CudaBackend
-                self._grad_backend = CudaBackend(self.geometry, self._device)
+        self._aux_backend()
         angles = np.asarray(angles, dtype=np.float64).reshape(-1, 3)
         n = angles.shape[0]
         if cor_shift is None:
