@@ -325,6 +325,13 @@ def test_host_buffer_entry_points_match_device_path():
     f_dev = be.forward(torch.as_tensor(vol)).cpu()
     b_dev = be.adjoint(torch.as_tensor(y)).cpu()
     g_dev = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(y), want_dproj=False)
+    # queued volume download: valid after sync_host(); the uploaded volume stays usable by the next operator (vol_dev)
+    be.forward_host(torch.as_tensor(vol).pin_memory())
+    out_q = torch.zeros((40, 36, 44), dtype=torch.float32).pin_memory()
+    be.adjoint_host(torch.as_tensor(y).pin_memory(), out_host=out_q, wait=False)
+    g6_q, c_q = be.proj_grad_host(None, torch.as_tensor(y).pin_memory(), vol_dev=be._buf("vol", be.vol_shape))
+    be.sync_host()
+    assert torch.equal(out_q, b_dev) and torch.equal(g6_q, g_dev["grad6"].cpu()) and torch.equal(c_q, g_dev["cost"].cpu())
     for chunk in (None, 3, 11, 50):
         f_h = be.forward_host(torch.as_tensor(vol).pin_memory(), chunk_views=chunk)
         assert f_h.device.type == "cpu" and torch.equal(f_h.reshape(f_dev.shape), f_dev)

@@ -126,3 +126,50 @@ def test_two_rank_solvers_match_single_process():
             assert rel_l2(rec_r.ravel(), rec.ravel()) < 2e-5, name
             np.testing.assert_allclose(err_r, err, rtol=1e-4, err_msg=name)
         assert np.array_equal(out[0][name][0], out[1][name][0]), name      # replicated state stays bitwise identical
+
+
+def _worker_guards(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tomography_alignment_b200.recon import SIRT
+        from tomography_alignment_b200.sharding import SharedHostBuffer
+        g, og = make_geoms((6, 6, 6), (6, 6), 1)
+        res = {}
+        # more ranks than views: every rank raises the same error before any collective (nobody is left waiting)
+        try:
+            ShardedProjector(g, phi=np.array([0.3]), backend_factory=OracleBackend)
+            res["sharded"] = "no error"
+        except ValueError as e:
+            res["sharded"] = str(e)
+        try:
+            SIRT(g, np.zeros((1, g.n_det), np.float32), np.zeros((1, 3)), np.zeros((1, 3)), group=dist.group.WORLD,
+                 backend=OracleBackend(g))
+            res["sirt"] = "no error"
+        except ValueError as e:
+            res["sirt"] = str(e)
+        # group=None inside an initialised job = an independent reconstruction per rank: no sharding, no collective
+        s = SIRT(g, np.ones((1, g.n_det), np.float32), np.zeros((1, 3)), np.zeros((1, 3)), group=None, backend=OracleBackend(g))
+        res["independent_world"] = s.world
+        # host buffer every rank sees: each rank writes its rows, rank 0 reads all of them
+        buf = SharedHostBuffer("tomo_b200_test_%d" % port, (world, 5))
+        buf.tensor[rank] = float(rank + 1)
+        dist.barrier()
+        res["shared"] = buf.tensor.clone().numpy()
+        dist.barrier()
+        buf.close()
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_empty_shards_are_refused_collectively_and_shared_host_buffer():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_guards, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        assert "every rank needs at least one view" in out[r]["sharded"] and "every rank needs at least one view" in out[r]["sirt"]
+        assert out[r]["independent_world"] == 1
+        assert np.array_equal(out[r]["shared"], np.array([[1.0] * 5, [2.0] * 5], np.float32))
