@@ -91,12 +91,14 @@ TOMO_API int tomo_views_upload(const TomoGeom* geom, const double* poses, int n_
 #define TOMO_KINDS_SEPARABLE   4     /* untilted views (alpha = beta = 0): separable kernels */
 #define TOMO_KINDS_TILE        8     /* tilted views inside the scatter envelope: adjoint_tile_kernel */
 #define TOMO_KINDS_UNCOLOURED 16     /* views outside it (rays nearly parallel to z): adjoint_gather_kernel */
+#define TOMO_KINDS_ZQUAD      32     /* nearly untilted views (W ~ (0,0,1)): zq_kernel_forward / zq_kernel_gradient */
 TOMO_API int tomo_views_kinds(const double* views_host, int n_proj);
 
 /* ---- padded volume -------------------------------------------------------------------------- */
 /* The ray-driven kernels read a zero-bordered copy of the volume (zero-padded-corner semantics of
  * src/ray_wt_grad.f90:35-89 without per-corner branches): [nx+2P][ny+2P][nzp], nzp = nz+2P rounded
- * up to 32 floats, data at offset (P,P,P), P = TOMO_PAD. */
+ * up to 32 floats, data at offset (P,P,P), P = TOMO_PAD; the buffer holds 32 floats of zero slack before and after it
+ * (tomo_padded_volume_bytes() includes them, tomo_pad_volume writes them). */
 TOMO_API size_t tomo_padded_volume_bytes(const TomoGeom* geom);
 TOMO_API int tomo_pad_volume(const TomoGeom* geom, const float* vol_dev, float* volpad_dev, void* stream);
 

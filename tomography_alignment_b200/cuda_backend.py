@@ -146,15 +146,15 @@ class CudaBackend(object):
     def _count(self, op):
         """Kernels one call of ``op`` launches for the current table (bench.py reports the total)."""
         k = self.kinds
-        gen, sep = bool(k & 2) or not k, bool(k & 4) or not k
+        gen, sep, zq = bool(k & 2) or not k, bool(k & 4) or not k, bool(k & 32) or not k
         if op == "forward":
-            return int(gen) + int(sep)
+            return int(gen) + int(sep) + int(zq)
         if op == "adjoint":
             tile = bool(k & 8) or not k
             return int(tile) + int(bool(k & 16) or not k) + 2 * int(sep)
         if op == "grad":
-            return int(gen) + int(sep)
-        return (int(gen) + int(sep)) * 2            # grad + finalize passes
+            return int(gen) + int(sep) + int(zq)
+        return (int(gen) + int(sep) + int(zq)) * 2   # grad + finalize passes
 
     # -- operators -----------------------------------------------------------------------------
     def pad(self, vol):
