@@ -292,13 +292,13 @@ def run_b200(a):
     L = be.lib
 
     def k_fwd():
-        _lib.check(L.tomo_forward(be._g(), ctypes.c_void_p(be.views.data_ptr()), my_n, ctypes.c_void_p(volpad.data_ptr()),
-                                  ctypes.c_void_p(proj.data_ptr()), be._stream()), "tomo_forward")
+        _lib.check(L.tomo_forward_ex(be._g(), ctypes.c_void_p(be.views.data_ptr()), my_n, be.kinds, ctypes.c_void_p(volpad.data_ptr()),
+                                     ctypes.c_void_p(proj.data_ptr()), be._stream()), "tomo_forward")
 
     def k_back():
-        _lib.check(L.tomo_back_adjoint(be._g(), ctypes.c_void_p(be.views.data_ptr()), my_n,
-                                       ctypes.c_void_p(meas.data_ptr()), ctypes.c_void_p(bp.data_ptr()), 0, be._stream()),
-                   "tomo_back_adjoint")
+        _lib.check(L.tomo_back_adjoint_slab(be._g(), ctypes.c_void_p(be.views.data_ptr()), my_n, be.kinds,
+                                            ctypes.c_void_p(meas.data_ptr()), ctypes.c_void_p(bp.data_ptr()), 0, None, 0, 0, n,
+                                            be._stream()), "tomo_back_adjoint")
 
     def k_grad():
         be.proj_grad(vol, meas=meas, want_proj=False, want_dproj=False, repad=False)
@@ -322,13 +322,13 @@ def run_b200(a):
     ach = kernels[dom][1] / (kernels[dom][0] * 1e-3) / 1e9
     # measured DRAM traffic of the dominant kernel (ncu --set full capture of this exact workload, profiles/)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic_512x720.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic_512x720.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         w = tj.get("workload", {})
         if (w.get("size"), w.get("views"), w.get("n_gpus")) == (n, n_proj, world):
             traffic = tj["kernels"].get(dom, {}).get("traffic_bytes")
-            traffic_src = "profiles/r1_traffic_512x720.json"
+            traffic_src = "profiles/r2_traffic_512x720.json"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": kernels[dom][1], "peak_source": peak_src,

@@ -17,14 +17,16 @@
  *   projections   float32 [n_proj][ndx][ndz], iz fastest       utilities/geometry.py:90-94,
  *                                                              utilities/projection_operators.py:108
  *   poses         float64 [n_proj][TOMO_POSE_STRIDE = 12] = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z,
- *                 n_samples, r_length0, reserved
+ *                 n_samples, r_length0, flags
  *                 (angles, xyz_shift and Geometry.cor_shift rows of projection_operators.py:50-52,97-102;
  *                 only cor_x is used, ray_voxel_utilities.py:72-73).  n_samples / r_length0 are the
  *                 reference's n = int(r_length[0] / step_size) and r_length[0] (ray_voxel_utilities.py:85-88)
  *                 as ITS numpy expression evaluates them: the quotient sits on an integer, so the count
  *                 depends on last-bit rounding that only the caller's numpy can reproduce.  n_samples <= 0
  *                 asks the library to evaluate the formula itself in float64 (may differ by one trailing
- *                 sample, which lies sy - step beyond the rotation centre).
+ *                 sample, which lies sy - step beyond the rotation centre).  flags != 0 lets a nearly untilted view
+ *                 take the z-quad ray kernels (four z-adjacent rays per thread, 128-bit window loads; same results to
+ *                 rounding, measured slower than the per-ray kernels on B200 -- off by default).
  *   gradients     order [tx, ty, tz, phi, alpha, beta]         utilities/ray_voxel_utilities.py:39-46
  */
 #ifndef TOMO_B200_H
@@ -91,12 +93,14 @@ TOMO_API int tomo_views_upload(const TomoGeom* geom, const double* poses, int n_
 #define TOMO_KINDS_SEPARABLE   4     /* untilted views (alpha = beta = 0): separable kernels */
 #define TOMO_KINDS_TILE        8     /* tilted views inside the scatter envelope: adjoint_tile_kernel */
 #define TOMO_KINDS_UNCOLOURED 16     /* views outside it (rays nearly parallel to z): adjoint_gather_kernel */
+#define TOMO_KINDS_ZQUAD      32     /* nearly untilted views (W ~ (0,0,1)): zq_kernel_forward / zq_kernel_gradient */
 TOMO_API int tomo_views_kinds(const double* views_host, int n_proj);
 
 /* ---- padded volume -------------------------------------------------------------------------- */
 /* The ray-driven kernels read a zero-bordered copy of the volume (zero-padded-corner semantics of
  * src/ray_wt_grad.f90:35-89 without per-corner branches): [nx+2P][ny+2P][nzp], nzp = nz+2P rounded
- * up to 32 floats, data at offset (P,P,P), P = TOMO_PAD. */
+ * up to 32 floats, data at offset (P,P,P), P = TOMO_PAD; the buffer holds 32 floats of zero slack before and after it
+ * (tomo_padded_volume_bytes() includes them, tomo_pad_volume writes them). */
 TOMO_API size_t tomo_padded_volume_bytes(const TomoGeom* geom);
 TOMO_API int tomo_pad_volume(const TomoGeom* geom, const float* vol_dev, float* volpad_dev, void* stream);
 

@@ -7,20 +7,27 @@
 #include "../../tomography_alignment_b200/csrc/ray_core.h"
 #include "../../tomography_alignment_b200/csrc/back_core.h"
 #include "../../tomography_alignment_b200/csrc/sep_core.h"
+#include "../../tomography_alignment_b200/csrc/zq_core.h"
 
 #define EMU_API extern "C" __attribute__((visibility("default")))
 
 EMU_API void emu_pad(const TomoGeom* g, const float* vol, float* pad)
 {
     const int nyp = g->ny + 2 * TOMO_PAD, nzp = tomo_nzp(g->nz), nxp = g->nx + 2 * TOMO_PAD;
-    for (size_t i = 0; i < (size_t)nxp * nyp * nzp; ++i) pad[i] = 0.f;
+    for (size_t i = 0; i < (size_t)nxp * nyp * nzp + TOMO_PAD_HEAD + TOMO_PAD_TAIL; ++i) pad[i] = 0.f;
+    pad += TOMO_PAD_HEAD;                                  // buffer layout of tomo_pad_volume: head slack, volume, tail slack
     for (int x = 0; x < g->nx; ++x) for (int y = 0; y < g->ny; ++y) for (int z = 0; z < g->nz; ++z)
         pad[((size_t)(x + TOMO_PAD) * nyp + y + TOMO_PAD) * nzp + z + TOMO_PAD] = vol[((size_t)x * g->ny + y) * g->nz + z];
 }
 
-EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, const float* volpad,
+// use_zq: take the z-quad core (zq_core.h) for the views that qualify (V_ZQ), as the CUDA path does
+static int g_use_zq = 1;
+EMU_API void emu_set_zq(int on) { g_use_zq = on; }
+
+EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, const float* volpad_buf,
                            const float* meas, float* proj, float* dproj, double* grad6, double* cost, int want_grad)
 {
+    const float* volpad = volpad_buf + TOMO_PAD_HEAD;
     const RayDims dm = {g->nx, g->ny, g->nz, (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz), tomo_nzp(g->nz)};
     const size_t n_det = (size_t)g->ndx * g->ndz;
     for (int v = 0; v < n_proj; ++v) {
@@ -83,13 +90,24 @@ EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, c
             if (cost) cost[v] = red[6];
             continue;
         }
+        const bool zq = g_use_zq && V[V_ZQ] != 0.0;
 #pragma omp parallel for schedule(dynamic, 8)
         for (int ix = 0; ix < g->ndx; ++ix) {
             double loc[7] = {0, 0, 0, 0, 0, 0, 0};
+            ZqSums zs;
+            unsigned short ev[ZQ_CAP + 2 * ZQ_G];
             for (int iz = 0; iz < g->ndz; ++iz) {
                 const size_t ray = (size_t)ix * g->ndz + iz;
                 RaySums s;
-                if (want_grad) ray_march<true>(volpad, V, dm, ix, iz, s); else ray_march<false>(volpad, V, dm, ix, iz, s);
+                if (zq) {                                   // one "thread" per group of four rays
+                    if (iz % ZQ_G == 0) {
+                        const int nr = g->ndz - iz < ZQ_G ? g->ndz - iz : ZQ_G;
+                        if (want_grad) zq_march<true>(volpad, V, dm, ix, iz, nr, ev, 1, zs); else zq_march<false>(volpad, V, dm, ix, iz, nr, ev, 1, zs);
+                    }
+                    const int k = iz % ZQ_G;
+                    s.acc = zs.acc[k];
+                    for (int a = 0; a < 3; ++a) { s.s0[a] = zs.s0[k][a]; s.s1[a] = zs.s1[k][a]; }
+                } else if (want_grad) ray_march<true>(volpad, V, dm, ix, iz, s); else ray_march<false>(volpad, V, dm, ix, iz, s);
                 if (proj) proj[v * n_det + ray] = s.acc;
                 if (want_grad) {
                     float dp[6];

@@ -111,8 +111,9 @@ class OracleBackend(_HostBackendBase):
 class EmuBackend(_HostBackendBase):
     """Same arithmetic as the CUDA kernels, executed by tests/emu/libtomo_emu.so on the CPU."""
 
-    def __init__(self, geometry):
+    def __init__(self, geometry, zquad=False):
         super().__init__(geometry)
+        self.zquad = zquad          # let qualifying views take the z-quad core (csrc/zq_core.h), as CudaBackend(zquad=True) does
         self.L = _lib.load()
         self.E = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libtomo_emu.so"))
         self.cg = geometry.to_c()
@@ -121,7 +122,8 @@ class EmuBackend(_HostBackendBase):
     def set_poses(self, poses):
         super().set_poses(poses)
         self.views = np.zeros((self.n_proj, _lib.VIEW_STRIDE))
-        full = self.poses12 if self.poses12 is not None else full_pose_table(self.geometry, self.poses)
+        full = self.poses12 if self.poses12 is not None else full_pose_table(self.geometry, self.poses,
+                                                                             flags=1.0 if self.zquad else 0.0)
         rc = self.L.tomo_views_compute_host(ctypes.byref(self.cg), _P(full), self.n_proj, _P(self.views))
         _lib.check(rc, "tomo_views_compute_host")
 

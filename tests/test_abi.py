@@ -47,9 +47,9 @@ def test_struct_layout_and_size_queries():
     g = TomoGeom()
     g.nx, g.ny, g.nz, g.ndx, g.ndz = 30, 20, 10, 30, 10
     nzp = ((10 + 2 * _lib.PAD + 31) // 32) * 32
-    assert L.tomo_padded_volume_bytes(ctypes.byref(g)) == 4 * (30 + 4) * (20 + 4) * nzp
+    assert L.tomo_padded_volume_bytes(ctypes.byref(g)) == 4 * ((30 + 4) * (20 + 4) * nzp + 64)      # + 32 floats of slack before and after
     # block partials of the generic kernel (8 x 32 ray tiles) + of the separable kernel (8 ix x z chunks)
-    assert L.tomo_proj_grad_workspace_bytes(ctypes.byref(g), 3) == 8 * 7 * (((30 + 7) // 8) * 1 + ((30 + 7) // 8) * 1) * 3
+    assert L.tomo_proj_grad_workspace_bytes(ctypes.byref(g), 3) == 8 * 7 * (((30 + 7) // 8) * 1 + ((30 + 7) // 8) * 1 + ((30 + 31) // 32) * 1) * 3   # generic + separable + z-quad tiles
 
 
 def test_library_is_sm100a_only():

@@ -687,3 +687,52 @@ def test_orphan_forward_project_on_gpu():
     pm = ProjectionMatrix(g, device="cuda:0")
     ax = pm.forward_project(rec, alpha, beta, phi, xyz, cor_shift=g.cor_shift)
     assert ax.shape == (n_proj, g.n_det) and rel_l2(ax, O.forward_project_orphan(og, rec, alpha, beta, phi, xyz)) <= TOL_PROJ
+
+
+@pytest.mark.parametrize("shape,dshape,n_proj,kw", [((40, 36, 44), (40, 44), 5, dict()), ((33, 19, 35), (33, 35), 3, dict(tilt=0.03, cor=[0.4, 0, 0])),
+                                                      ((64, 64, 70), (70, 66), 4, dict(tilt=0.05, shift=4.0)), ((16, 16, 16), (16, 16), 4, dict(step=0.5))])
+def test_zquad_kernels_vs_oracle(shape, dshape, n_proj, kw):
+    """CudaBackend(zquad=True): zq_kernel_forward / zq_kernel_gradient (four z-adjacent rays per thread, 128-bit window loads,
+    csrc/zq_core.h) against the oracle and against the default per-ray kernels; bitwise repeatable."""
+    from tomography_alignment_b200.cuda_backend import CudaBackend
+    g, og, be0, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)
+    be = CudaBackend(g, "cuda:0", zquad=True)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    assert be.kinds == (1 | 8 | 32) and be0.kinds == (1 | 2 | 8)
+    rng = np.random.default_rng(2)
+    vol = rng.random(shape).astype(np.float32)
+    meas = (op.forward(vol) * 1.02 + 0.05).astype(np.float32)
+    f = be.forward(torch.as_tensor(vol))
+    assert rel_l2(f.cpu().numpy().reshape(n_proj, -1), op.forward(vol)) <= TOL_PROJ
+    out = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(meas))
+    ref = be0.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(meas))
+    for i in range(n_proj):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["proj"][i].cpu().numpy(), p) <= TOL_PROJ and rel_l2(out["dproj"][i].cpu().numpy(), gr) <= TOL_GRAD
+        res = meas[i].astype(np.float64) - p
+        assert rel_l2(out["grad6"][i].cpu().numpy(), -gr @ res) <= TOL_GRAD
+    assert rel_l2(out["grad6"].cpu().numpy(), ref["grad6"].cpu().numpy()) <= 1e-5
+    for _ in range(2):
+        assert torch.equal(be.forward(torch.as_tensor(vol)), f)
+        o2 = be.proj_grad(torch.as_tensor(vol), meas=torch.as_tensor(meas))
+        assert torch.equal(o2["grad6"], out["grad6"]) and torch.equal(o2["dproj"], out["dproj"])
+
+
+def test_zquad_kernels_at_256_cubed():
+    """The z-quad kernels at a BASELINE size: 256^3, 4 views of benchmark_poses(360), full outputs against the oracle."""
+    from tomography_alignment_b200.cuda_backend import CudaBackend
+    n, sel = 256, [3, 100, 181, 300]
+    g, og = make_geoms((n, n, n), (n, n), len(sel))
+    phi, alpha, beta, xyz = (a[sel] for a in benchmark_poses(360))
+    be = CudaBackend(g, "cuda:0", zquad=True)
+    be.set_poses(pose_table(np.array([phi, alpha, beta]).T, xyz, g.cor_shift))
+    assert be.kinds & 32
+    vol_d = torch.rand((n, n, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    vol = vol_d.cpu().numpy()
+    fwd = be.forward(vol_d)
+    out = be.proj_grad(vol_d)
+    rays = np.arange(og.n_det)
+    for k in range(len(sel)):
+        p, gr = O.forward_proj_grad_rays(og, alpha[k], beta[k], phi[k], xyz[k], og.cor_shift[k], vol, rays)
+        assert rel_l2(fwd[k].cpu().numpy(), p) <= TOL_PROJ and rel_l2(out["proj"][k].cpu().numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][k].cpu().numpy(), gr) <= TOL_GRAD

@@ -35,7 +35,7 @@ extern "C" int tomo_views_kinds(const double* views_host, int n_proj)
     for (int v = 0; v < n_proj; ++v) {
         const double* V = views_host + (size_t)v * TOMO_VIEW_STRIDE;
         const bool sep = V[V_SEP] != 0.0, col = V[V_NCOL] != 0.0;
-        kinds |= sep ? TOMO_KINDS_SEPARABLE : TOMO_KINDS_GENERIC;
+        kinds |= sep ? TOMO_KINDS_SEPARABLE : (V[V_ZQ] != 0.0 ? TOMO_KINDS_ZQUAD : TOMO_KINDS_GENERIC);
         if (!col) kinds |= TOMO_KINDS_UNCOLOURED;
         else if (!sep) kinds |= TOMO_KINDS_TILE;
     }

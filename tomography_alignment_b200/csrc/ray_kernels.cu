@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include "tomo_common.h"
 #include "ray_core.h"
+#include "zq_core.h"
 
 namespace {
 
@@ -45,6 +46,7 @@ struct RayArgs {
     int nxt, nzt;            // detector tiles along x and z
     int xparts, xpp;         // launch order: bands of xpp x-tiles (see ray_kernel_body)
     int skip_separable;      // leave views with V_SEP == 1 to the separable kernels
+    int skip_zq;             // leave views with V_ZQ == 1 to the z-quad kernels
 };
 
 template <bool GRAD>
@@ -67,6 +69,7 @@ __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
 
     const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
     if (A.skip_separable && V[V_SEP] != 0.0) return;               // untilted view (block-uniform): the separable kernels do it
+    if (A.skip_zq && V[V_ZQ] != 0.0) return;                       // nearly untilted view: the z-quad kernels do it
     const size_t n_det = (size_t)A.ndx * A.ndz;
     const size_t ray = (size_t)ix * A.ndz + iz;
 
@@ -120,16 +123,115 @@ __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
 __global__ void __launch_bounds__(TILE_Z * TILE_X, 40 / TILE_X) ray_kernel_forward(const RayArgs A) { ray_kernel_body<false>(A); }
 __global__ void __launch_bounds__(TILE_Z * TILE_X) ray_kernel_gradient(const RayArgs A) { ray_kernel_body<true>(A); }
 
+// ---- z-quad kernels (zq_core.h): a thread owns four z-adjacent rays -------------------------------------------------
+// Block = 8 warps; a warp covers 4 detector columns x 32 rows (8 lanes of 4 rays per column), a block 32 columns x 32 rows.
+// Launch order as above (z-tile, band of columns, view, x-tile within the band) with the tile sizes below.
+#ifndef ZQ_NTHREADS
+#define ZQ_NTHREADS 256
+#endif
+constexpr int ZQ_THREADS = ZQ_NTHREADS, ZQ_TILE_X = ZQ_THREADS / 8, ZQ_TILE_Z = 32;
+#ifndef ZQ_BAND_COLS
+#define ZQ_BAND_COLS 128             // detector columns per band of the launch order
+#endif
+#define ZQ_BAND_TILES (ZQ_BAND_COLS / ZQ_TILE_X)
+
+template <bool GRAD>
+__device__ __forceinline__ void zq_kernel_body(const RayArgs& A)
+{
+    __shared__ unsigned short ev[ZQ_CAP + 2 * ZQ_G][ZQ_THREADS];     // per-thread event lists + clip ranges, interleaved (conflict-free)
+    const int pb   = blockIdx.x;
+    const int xl   = pb % A.xpp;
+    const int view = (pb / A.xpp) % A.n_proj;
+    const int part = (pb / (A.xpp * A.n_proj)) % A.xparts;
+    const int zt   = pb / (A.xpp * A.n_proj * A.xparts);
+    const int xt   = part * A.xpp + xl;
+    if (xt >= A.nxt) return;                                       // block-uniform (last part may be ragged)
+    const double* __restrict__ V = A.views + (size_t)view * TOMO_VIEW_STRIDE;
+    if (V[V_ZQ] == 0.0) return;                                    // block-uniform: another kernel family owns this view
+    const int bid  = (zt * A.n_proj + view) * A.nxt + xt;          // logical tile id: layout of the block partials
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ix = xt * ZQ_TILE_X + warp * 4 + (lane >> 3);
+    const int iz0 = zt * ZQ_TILE_Z + (lane & 7) * ZQ_G;
+    int nrays = 0;
+    if (ix < A.ndx) nrays = min(ZQ_G, max(0, A.ndz - iz0));
+    const size_t n_det = (size_t)A.ndx * A.ndz;
+    const RayDims dm = {A.nx, A.ny, A.nz, A.sxp, A.syp};
+
+    ZqSums s;
+    zq_march<GRAD>(A.volpad, V, dm, ix, iz0, nrays, &ev[0][tid], ZQ_THREADS, s);
+
+    const size_t ray0 = (size_t)ix * A.ndz + iz0;
+    if (A.proj) {
+        float* __restrict__ o = A.proj + (size_t)view * n_det + ray0;
+        if (nrays == ZQ_G && ((A.ndz & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(s.acc[0], s.acc[1], s.acc[2], s.acc[3]);
+        else
+#pragma unroll
+            for (int k = 0; k < ZQ_G; ++k) if (k < nrays) o[k] = s.acc[k];
+    }
+    if (GRAD) {
+        double red[NRED] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < ZQ_G; ++k) {
+            if (k < nrays) {
+                RaySums r;
+                r.acc = s.acc[k];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { r.s0[a] = s.s0[k][a]; r.s1[a] = s.s1[k][a]; }
+                float dp[6];
+                ray_gradient(V, ix, iz0 + k, r, dp);
+                if (A.dproj) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) A.dproj[((size_t)view * 6 + c) * n_det + ray0 + k] = dp[c];
+                }
+                if (A.meas) {
+                    const double res = (double)A.meas[(size_t)view * n_det + ray0 + k] - (double)r.acc;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) red[c] += -(double)dp[c] * res;
+                    red[6] += 0.5 * res * res;
+                }
+            }
+        }
+        if (A.partial) {       // fixed-order block reduction: the thread's four rays, shuffle tree, then warps in order
+            __shared__ double sm[ZQ_THREADS / 32][NRED];
+#pragma unroll
+            for (int c = 0; c < NRED; ++c) {
+                double v = red[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (lane == 0) sm[warp][c] = v;
+            }
+            __syncthreads();
+            if (tid < NRED) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < ZQ_THREADS / 32; ++w) v += sm[w][tid];
+                A.partial[(size_t)bid * NRED + tid] = v;
+            }
+        }
+    }
+}
+
+#ifndef ZQ_FWD_MINB
+#define ZQ_FWD_MINB 2
+#endif
+#ifndef ZQ_GRAD_MINB
+#define ZQ_GRAD_MINB 2
+#endif
+__global__ void __launch_bounds__(ZQ_THREADS, ZQ_FWD_MINB) zq_kernel_forward(const RayArgs A) { zq_kernel_body<false>(A); }
+__global__ void __launch_bounds__(ZQ_THREADS, ZQ_GRAD_MINB) zq_kernel_gradient(const RayArgs A) { zq_kernel_body<true>(A); }
+
 // Second pass of the deterministic reduction: one thread per (view, component) sums the block
 // partials of that view in (zt, xt) order.
-__global__ void grad_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ views, int want_sep,
+__global__ void grad_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ views, int kind,
                                      int n_proj, int nxt, int nzt, double* __restrict__ grad6, double* __restrict__ cost)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_proj * NRED) return;
     const int view = t / NRED, k = t % NRED;
-    // tilted views were reduced by ray_kernel_gradient, untilted ones by sep_gradient_kernel (own tiling)
-    if ((views[(size_t)view * TOMO_VIEW_STRIDE + V_SEP] != 0.0) != (want_sep != 0)) return;
+    // kind 0: views reduced by ray_kernel_gradient, 1: by sep_gradient_kernel, 2: by zq_kernel_gradient (each with its own tiling)
+    const double* __restrict__ V = views + (size_t)view * TOMO_VIEW_STRIDE;
+    const int mine = (V[V_SEP] != 0.0) ? 1 : (V[V_ZQ] != 0.0) ? 2 : 0;
+    if (mine != kind) return;
     double v = 0.0;
     for (int zt = 0; zt < nzt; ++zt)
         for (int xt = 0; xt < nxt; ++xt)
@@ -141,16 +243,18 @@ __global__ void grad_finalize_kernel(const double* __restrict__ partial, const d
 __global__ void pad_volume_kernel(const float* __restrict__ vol, float* __restrict__ pad,
                                   int nx, int ny, int nz, int nyp, int nzp)
 {
-    // one thread per padded element, z fastest
-    const size_t total = (size_t)(nx + 2 * TOMO_PAD) * nyp * nzp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    // one thread per buffer element (TOMO_PAD_HEAD zeros, the padded volume z fastest, TOMO_PAD_TAIL zeros)
+    const size_t body = (size_t)(nx + 2 * TOMO_PAD) * nyp * nzp, total = body + TOMO_PAD_HEAD + TOMO_PAD_TAIL;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (size_t)gridDim.x * blockDim.x) {
+        if (b < TOMO_PAD_HEAD || b >= body + TOMO_PAD_HEAD) { pad[b] = 0.f; continue; }
+        const size_t i = b - TOMO_PAD_HEAD;
         const int zp = (int)(i % nzp);
         const size_t r = i / nzp;
         const int yp = (int)(r % nyp), xp = (int)(r / nyp);
         const int x = xp - TOMO_PAD, y = yp - TOMO_PAD, z = zp - TOMO_PAD;
         float v = 0.f;
         if (x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz) v = vol[((size_t)x * ny + y) * nz + z];
-        pad[i] = v;
+        pad[b] = v;
     }
 }
 
@@ -174,7 +278,7 @@ static int check_sizes(const TomoGeom* g)
 extern "C" size_t tomo_padded_volume_bytes(const TomoGeom* g)
 {
     if (!g) return 0;
-    return sizeof(float) * (size_t)(g->nx + 2 * TOMO_PAD) * (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz);
+    return sizeof(float) * ((size_t)(g->nx + 2 * TOMO_PAD) * (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz) + TOMO_PAD_HEAD + TOMO_PAD_TAIL);
 }
 
 extern "C" int tomo_pad_volume(const TomoGeom* g, const float* vol, float* pad, void* stream)
@@ -193,8 +297,8 @@ static int fill_args(const TomoGeom* g, const void* views, int n_proj, const flo
 {
     if (!g || !views || !volpad || n_proj <= 0) { tomo_set_error("ray operator: null pointer or n_proj <= 0"); return TOMO_E_ARG; }
     if (int e = check_sizes(g)) return e;
-    A->volpad = volpad; A->views = (const double*)views;
-    A->meas = nullptr; A->proj = nullptr; A->dproj = nullptr; A->partial = nullptr; A->skip_separable = 0;
+    A->volpad = volpad + TOMO_PAD_HEAD; A->views = (const double*)views;      // the padded volume proper starts behind the head slack
+    A->meas = nullptr; A->proj = nullptr; A->dproj = nullptr; A->partial = nullptr; A->skip_separable = 0; A->skip_zq = 0;
     A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz; A->n_proj = n_proj;
     A->syp = tomo_nzp(g->nz);
     A->sxp = (g->ny + 2 * TOMO_PAD) * A->syp;
@@ -207,6 +311,16 @@ static int fill_args(const TomoGeom* g, const void* views, int n_proj, const flo
     const double nblocks = (double)A->xpp * A->xparts * A->nzt * n_proj;
     if (nblocks >= 2147483647.0) { tomo_set_error("too many detector tiles for one launch"); return TOMO_E_RANGE; }
     return 0;
+}
+
+// tile counts and launch order of the z-quad kernels
+static void zq_tiling(const TomoGeom* g, int n_proj, RayArgs* Z)
+{
+    (void)n_proj;
+    Z->nxt = (g->ndx + ZQ_TILE_X - 1) / ZQ_TILE_X;
+    Z->nzt = (g->ndz + ZQ_TILE_Z - 1) / ZQ_TILE_Z;
+    Z->xparts = (Z->nxt + ZQ_BAND_TILES - 1) / ZQ_BAND_TILES;
+    Z->xpp = (Z->nxt + Z->xparts - 1) / Z->xparts;
 }
 
 extern "C" int tomo_forward(const TomoGeom* g, const void* views, int n_proj,
@@ -224,10 +338,19 @@ extern "C" int tomo_forward_ex(const TomoGeom* g, const void* views, int n_proj,
     A.proj = proj;
     A.skip_separable = 1;
     const bool known = (kinds & TOMO_KINDS_KNOWN) != 0;
+    // nearly untilted views (V_ZQ): z-quad kernel, which needs 16-byte aligned plane rows (128-bit loads)
+    const bool zq_ok = (((uintptr_t)A.volpad) & 15u) == 0;
+    A.skip_zq = zq_ok ? 1 : 0;
     const dim3 block(TILE_Z, TILE_X);
-    if (!known || (kinds & TOMO_KINDS_GENERIC)) {
+    if (!known || (kinds & TOMO_KINDS_GENERIC) || (!zq_ok && (kinds & TOMO_KINDS_ZQUAD))) {
         ray_kernel_forward<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
         if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_forward")) return e;
+    }
+    if (zq_ok && (!known || (kinds & TOMO_KINDS_ZQUAD))) {
+        RayArgs Z = A;
+        zq_tiling(g, n_proj, &Z);
+        zq_kernel_forward<<<Z.xpp * Z.xparts * Z.nzt * n_proj, ZQ_THREADS, 0, (cudaStream_t)stream>>>(Z);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "zq_kernel_forward")) return e;
     }
     // untilted views (alpha = beta = 0): separable kernel; both kernels return at once for views of the other kind
     if (!known || (kinds & TOMO_KINDS_SEPARABLE)) return tomo_forward_separable_launch(g, views, n_proj, volpad, proj, stream);
@@ -240,8 +363,9 @@ extern "C" size_t tomo_proj_grad_workspace_bytes(const TomoGeom* g, int n_proj)
     const size_t nxt = (g->ndx + TILE_X - 1) / TILE_X, nzt = (g->ndz + TILE_Z - 1) / TILE_Z;
     int sxt, sch;
     tomo_grad_separable_tiles(g, &sxt, &sch);
-    // block partials of ray_kernel_gradient followed by those of sep_gradient_kernel
-    return sizeof(double) * NRED * (nxt * nzt + (size_t)sxt * sch) * (size_t)n_proj;
+    const size_t zxt = (g->ndx + ZQ_TILE_X - 1) / ZQ_TILE_X, zzt = (g->ndz + ZQ_TILE_Z - 1) / ZQ_TILE_Z;
+    // block partials of ray_kernel_gradient followed by those of sep_gradient_kernel and of zq_kernel_gradient
+    return sizeof(double) * NRED * (nxt * nzt + (size_t)sxt * sch + zxt * zzt) * (size_t)n_proj;
 }
 
 extern "C" int tomo_proj_grad(const TomoGeom* g, const void* views, int n_proj,
@@ -271,14 +395,27 @@ extern "C" int tomo_proj_grad_ex(const TomoGeom* g, const void* views, int n_pro
     }
     A.skip_separable = 1;
     const bool known = (kinds & TOMO_KINDS_KNOWN) != 0;
-    const bool want_gen = !known || (kinds & TOMO_KINDS_GENERIC), want_sep = !known || (kinds & TOMO_KINDS_SEPARABLE);
+    const bool zq_ok = (((uintptr_t)A.volpad) & 15u) == 0;
+    A.skip_zq = zq_ok ? 1 : 0;
+    const bool want_gen = !known || (kinds & TOMO_KINDS_GENERIC) || (!zq_ok && (kinds & TOMO_KINDS_ZQUAD));
+    const bool want_sep = !known || (kinds & TOMO_KINDS_SEPARABLE);
+    const bool want_zq = zq_ok && (!known || (kinds & TOMO_KINDS_ZQUAD));
     const dim3 block(TILE_Z, TILE_X);
     if (want_gen) {
         ray_kernel_gradient<<<A.xpp * A.xparts * A.nzt * n_proj, block, 0, (cudaStream_t)stream>>>(A);
         if (int e = tomo_check_cuda(cudaGetLastError(), "ray_kernel_gradient")) return e;
     }
-    // untilted views: separable kernel with its own block partials behind the generic ones
+    // untilted views: separable kernel with its own block partials behind the generic ones; then the z-quad kernel's
     double* sep_partial = reduce ? A.partial + (size_t)NRED * A.nxt * A.nzt * n_proj : nullptr;
+    int sxt0, sch0;
+    tomo_grad_separable_tiles(g, &sxt0, &sch0);
+    RayArgs Z = A;
+    zq_tiling(g, n_proj, &Z);
+    Z.partial = reduce ? sep_partial + (size_t)NRED * sxt0 * sch0 * n_proj : nullptr;
+    if (want_zq) {
+        zq_kernel_gradient<<<Z.xpp * Z.xparts * Z.nzt * n_proj, ZQ_THREADS, 0, (cudaStream_t)stream>>>(Z);
+        if (int e = tomo_check_cuda(cudaGetLastError(), "zq_kernel_gradient")) return e;
+    }
     if (want_sep)
         if (int e = tomo_grad_separable_launch(g, views, n_proj, volpad, meas, proj, dproj, sep_partial, stream)) return e;
     if (reduce) {
@@ -289,6 +426,8 @@ extern "C" int tomo_proj_grad_ex(const TomoGeom* g, const void* views, int n_pro
             grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A.partial, A.views, 0, n_proj, A.nxt, A.nzt, grad6, cost);
         if (want_sep)
             grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sep_partial, A.views, 1, n_proj, sxt, sch, grad6, cost);
+        if (want_zq)
+            grad_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(Z.partial, A.views, 2, n_proj, Z.nxt, Z.nzt, grad6, cost);
         return tomo_check_cuda(cudaGetLastError(), "grad_finalize_kernel");
     }
     return 0;

@@ -279,7 +279,7 @@ int tomo_forward_separable_launch(const TomoGeom* g, const void* views, int n_pr
                                   void* stream)
 {
     SepArgs A;
-    A.volpad = volpad; A.views = (const double*)views; A.proj = proj;
+    A.volpad = volpad + TOMO_PAD_HEAD; A.views = (const double*)views; A.proj = proj;
     A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
     A.nzp = tomo_nzp(g->nz);
     A.syp = A.nzp;
@@ -336,7 +336,7 @@ int tomo_grad_separable_launch(const TomoGeom* g, const void* views, int n_proj,
                                float* proj, float* dproj, double* partial, void* stream)
 {
     SepGradArgs A;
-    A.volpad = volpad; A.views = (const double*)views; A.meas = meas; A.proj = proj; A.dproj = dproj; A.partial = partial;
+    A.volpad = volpad + TOMO_PAD_HEAD; A.views = (const double*)views; A.meas = meas; A.proj = proj; A.dproj = dproj; A.partial = partial;
     A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
     A.nzp = tomo_nzp(g->nz);
     A.syp = A.nzp;

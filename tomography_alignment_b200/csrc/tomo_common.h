@@ -37,10 +37,17 @@ enum {
     V_VBOK = 148,  // 1   1.0 when the detector footprint of a TOMO_VB_X x _Y x _Z voxel brick under the voxel-driven
                    //     transform fits the TOMO_VB_TX x TOMO_VB_TZ box the TMA-staged backprojector loads per view
     V_NVBIG = 149, // 1   number of views of the whole table with V_VBOK == 0 (same in every record)
-    V_END  = 150
+    V_ZQ   = 150,  // 1   1.0 when the view qualifies for the z-quad ray kernels (zq_core.h): W ~ (0, 0, 1), i.e. four z-adjacent
+                   //     rays share an (x, y) cell and sit in consecutive z cells for almost every sample
+    V_END  = 151
 };
 
 static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE");
+
+// Floats of slack before and after the padded volume inside its buffer (zeros): the z-quad kernels load aligned 8-plane
+// windows around cells up to a few planes beside the zero border (zq_core.h).  128 bytes keep the 16-byte alignment.
+#define TOMO_PAD_HEAD 32
+#define TOMO_PAD_TAIL 32
 
 // Row pitch (floats) of the padded volume along z.
 static inline

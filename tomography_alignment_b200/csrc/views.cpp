@@ -171,6 +171,12 @@ extern "C" int tomo_views_compute_host(const TomoGeom* g, const double* poses, i
         // untilted view: the z coordinate of a sample depends on iz only and (x, y) on (ix, j) only
         o[V_SEP] = (W.v[0] == 0.0 && W.v[1] == 0.0 && U.v[2] == 0.0 && D.v[2] == 0.0 && W.v[2] > 0.0) ? 1.0 : 0.0;
 
+        // z-quad ray kernels (zq_core.h), opt-in per view (pose column 11; measured slower than the per-ray kernels on B200,
+        // profiles/README.md): rays iz .. iz+3 of a detector column must almost always share an (x, y) cell (|3 W_xy| small)
+        // and sit in consecutive z cells (|3 (W_z - 1)| small); the sample index must fit 13 bits
+        o[V_ZQ] = (ps[11] != 0.0 && o[V_SEP] == 0.0 && std::fabs(W.v[2] - 1.0) <= 0.02 && std::fabs(W.v[0]) <= 0.06 && std::fabs(W.v[1]) <= 0.06 &&
+                   n <= 8191 && n > 0) ? 1.0 : 0.0;
+
         // voxel-driven (inverse convention) transform  Ry (Rx Rz x + t)   (external_back_projection.f90:17-25)
         const M3 Vr = mul(Rb, mul(Ra, Rp));
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[V_VROT + 3 * i + j] = Vr.m[i][j];

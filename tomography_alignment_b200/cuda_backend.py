@@ -21,12 +21,15 @@ class CudaBackend(object):
     geometry on one GPU.  Volumes are float32 [nx, ny, nz] (z fastest), projections float32
     [n_proj, ndx, ndz] (iz fastest): the reference's layouts (include/tomo_b200.h)."""
 
-    def __init__(self, geometry, device=None):
+    def __init__(self, geometry, device=None, zquad=False):
         if not torch.cuda.is_available():
             raise _lib.TomoError("tomography_alignment_b200 needs a CUDA device (B200, sm_100a); "
                                  "there is no CPU fallback for the projection operators")
         self.lib = _lib.load()
         self.geometry = geometry
+        # zquad=True: nearly untilted views take the z-quad forward / gradient kernels (csrc/zq_core.h: four z-adjacent rays
+        # per thread, 128-bit loads).  Same results to rounding; measured slower than the per-ray kernels on B200, hence off.
+        self.zquad = bool(zquad)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.cgeom = geometry.to_c()
         self.vol_shape = tuple(int(v) for v in geometry.vox_shape)
@@ -122,7 +125,7 @@ class CudaBackend(object):
         """poses: float64 (n_proj, 9) = phi, alpha, beta, tx, ty, tz, cor_x, cor_y, cor_z (``pose_table``); the
         reference's per-view sample count is appended here (``full_pose_table``)."""
         from .projection_operators import full_pose_table
-        poses = full_pose_table(self.geometry, poses)
+        poses = full_pose_table(self.geometry, poses, flags=1.0 if self.zquad else 0.0)
         n = poses.shape[0]
         # always a fresh table: operators returned by earlier projection_matrix() calls keep (and re-bind) theirs
         host = np.empty((n, _lib.VIEW_STRIDE), dtype=np.float64)
@@ -146,15 +149,15 @@ class CudaBackend(object):
     def _count(self, op):
         """Kernels one call of ``op`` launches for the current table (bench.py reports the total)."""
         k = self.kinds
-        gen, sep = bool(k & 2) or not k, bool(k & 4) or not k
+        gen, sep, zq = bool(k & 2) or not k, bool(k & 4) or not k, bool(k & 32) or not k
         if op == "forward":
-            return int(gen) + int(sep)
+            return int(gen) + int(sep) + int(zq)
         if op == "adjoint":
             tile = bool(k & 8) or not k
             return int(tile) + int(bool(k & 16) or not k) + 2 * int(sep)
         if op == "grad":
-            return int(gen) + int(sep)
-        return (int(gen) + int(sep)) * 2            # grad + finalize passes
+            return int(gen) + int(sep) + int(zq)
+        return (int(gen) + int(sep) + int(zq)) * 2   # grad + finalize passes
 
     # -- operators -----------------------------------------------------------------------------
     def pad(self, vol):

@@ -104,9 +104,10 @@ def reference_sample_counts(geometry, poses):
     return out
 
 
-def full_pose_table(geometry, poses):
+def full_pose_table(geometry, poses, flags=0.0):
     """(n_proj, 9) rows of ``pose_table`` -> the (n_proj, TOMO_POSE_STRIDE = 12) records of the C ABI:
-    columns 9, 10 = the reference's sample count and r_length[0] (``reference_sample_counts``), 11 reserved."""
+    columns 9, 10 = the reference's sample count and r_length[0] (``reference_sample_counts``), 11 = per-view flags
+    (non-zero: the view may take the z-quad ray kernels)."""
     poses = np.asarray(poses, dtype=np.float64)
     poses = poses.reshape(-1, poses.shape[-1] if poses.ndim > 1 else 9)
     if poses.shape[1] == 12:
@@ -114,6 +115,7 @@ def full_pose_table(geometry, poses):
     full = np.zeros((poses.shape[0], 12), dtype=np.float64)
     full[:, :9] = poses[:, :9]
     full[:, 9:11] = reference_sample_counts(geometry, poses)
+    full[:, 11] = flags
     return full
 
 
