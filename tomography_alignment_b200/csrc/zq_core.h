@@ -88,10 +88,10 @@ TOMO_HD void zq_exact_sample(const float* __restrict__ vol, const double* __rest
         const double p = V[V_P00 + a] + (double)ix * V[V_U + a] + (double)iz * V[V_W + a];      // as ray_setup
         const double q = p + (double)j * V[V_D + a];
         const double qi = floor(q);
-        f[a] = (float)(q - qi);
-        int i = (int)qi;
-        if (f[a] >= 1.0f) { f[a] -= 1.0f; i += 1; }                                              // float32 rounding of 1 - eps
-        off += (TOMO_PAD + i) * ust[a];
+        // the cell is the float64 one (the gradient jumps across lattice planes): a fraction of 1 - 2e-8 must not round up
+        // into the next cell, it is clamped to the largest float32 below 1 instead
+        f[a] = fminf((float)(q - qi), 0.99999994f);
+        off += (TOMO_PAD + (int)qi) * ust[a];
     }
     const float* __restrict__ c = vol + off;
     const int o10 = dm.sxp, o01 = dm.syp, o11 = dm.sxp + dm.syp;

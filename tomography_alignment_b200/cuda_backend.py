@@ -42,6 +42,7 @@ class CudaBackend(object):
         self._ws = None
         self.launches = 0        # kernels of ours launched so far (bench.py reports the count)
         self._bound_state = None  # identity of the ProjectionOperator state whose poses are current
+        self._copy_out = None    # stream of queued result downloads (adjoint_host(wait=False))
         self._copy = None        # side stream for host<->device copies overlapped with the kernels
         self._dbuf = {}          # cached device staging buffers of the host-buffer entry points
         self.h2d_bytes = 0       # bytes moved by the host-buffer entry points (bench.py reports them)
@@ -274,6 +275,8 @@ class CudaBackend(object):
     def sync_host(self):
         """Wait until every copy queued by the ``*_host`` entry points has landed (for calls made with ``wait=False``)."""
         self._copy_stream().synchronize()
+        if self._copy_out is not None:
+            self._copy_out.synchronize()
         torch.cuda.current_stream(self.device).synchronize()
 
     def adjoint_host(self, y_host, out_host=None, chunk_views=None, to_host=True, wait=True):
@@ -316,10 +319,13 @@ class CudaBackend(object):
             return vol_d
         self.d2h_bytes += 4 * out_host.numel()
         if not wait:
+            # a stream of its own: on the upload stream the copy would sit in front of the next operator's input chunks
+            if self._copy_out is None:
+                self._copy_out = torch.cuda.Stream(device=self.device)
             done = torch.cuda.Event()
             done.record(cur)
-            with torch.cuda.stream(cp):
-                cp.wait_event(done)
+            with torch.cuda.stream(self._copy_out):
+                self._copy_out.wait_event(done)
                 out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
             return out_host
         out_host.reshape(-1).copy_(vol_d.reshape(-1), non_blocking=True)
