@@ -368,7 +368,10 @@ def run_b200(a):
 
         d_vol = torch.empty((n, n, n), dtype=torch.float32, device=dev)
         g_tab = torch.zeros((n_proj, 7), dtype=torch.float64, device=dev)
-        sharded_io = world > 1 and n % world == 0
+        # shared page-locked host buffers up to 8 GB in total (larger registrations were refused on the 8-GPU box at 1024^3:
+        # the per-process pinned path below is used then)
+        shared_bytes = 4.0 * (2 * n ** 3 + n_proj * n * n)
+        sharded_io = world > 1 and n % world == 0 and shared_bytes <= float(os.environ.get("TOMO_BENCH_SHARED_HOST_BYTES", 8e9))
         if sharded_io:
             # one box, one host memory: the volume, the backprojection and the projections live in host buffers every rank
             # sees (POSIX shared memory, page-locked in each process); each rank moves only its 1/N over its own PCIe link

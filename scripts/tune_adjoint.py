@@ -12,7 +12,7 @@ phi, alpha, beta, xyz = benchmark_poses(720)
 if os.environ.get("UNTILTED"):
     alpha, beta = alpha * 0, beta * 0
 sel = np.linspace(0, 719, n_proj).astype(int)
-be = CudaBackend(g, "cuda:0")
+be = CudaBackend(g, "cuda:0", zquad=bool(os.environ.get("ZQUAD")))
 be.set_poses(pose_table(np.array([phi, alpha, beta]).T[sel], xyz[sel], g.cor_shift))
 torch.manual_seed(0)
 vol = torch.rand((n, n, n), device="cuda")
@@ -26,7 +26,7 @@ def t(fn, reps=3):
     for _ in range(reps): fn()
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / reps
-out = {"lib": os.path.basename(os.environ.get("TOMO_B200_LIB", "default")), "n": n, "views": n_proj}
+out = {"lib": os.path.basename(os.environ.get("TOMO_B200_LIB", "default")), "n": n, "views": n_proj, "zquad": bool(os.environ.get("ZQUAD"))}
 if "f" in which: out["fwd_ms"] = t(lambda: be.forward(vol, out=proj))
 if "b" in which:
     out["back_ms"] = t(lambda: be.adjoint(y, out=bp))
