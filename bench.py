@@ -69,6 +69,8 @@ def parse():
     ap.add_argument("--slabs", type=int, default=1,
                     help="x-slabs of the backprojection (all-reduce of slab k under the kernel of slab k+1); 1 = one launch on a side "
                          "stream, its all-reduce hidden behind the gradient kernel (measured best: profiles/README.md)")
+    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
+                    help="view sharding for N > 1: interleaved (balanced) or the reference's contiguous np.array_split blocks")
     ap.add_argument("--host-phantom", action="store_true",
                     help="build the phantom with numpy on the host (profiling runs: keeps torch's phantom kernels out of ncu launch lists)")
     return ap.parse_args()
@@ -202,7 +204,10 @@ def run_b200(a):
     n, n_proj = a.size, a.views
     geo = Geometry(n_proj, np.array([n, n, n]), np.ones(3), np.array([n, n]), np.ones(2))
     phi, alpha, beta, xyz = benchmark_poses(n_proj)
-    mine = shard_views(n_proj, world, rank)
+    # interleaved shards (view i on rank i mod N): every rank sees the whole angular range, so the ranks stay balanced (the cost
+    # of a view depends on its angle; with the reference's contiguous np.array_split blocks every all-reduce waits 2.7 ms of
+    # 88 ms for the slowest rank at 8 GPUs, profiles/r2_shard_balance.json).  --shard contiguous restores the reference's split.
+    mine = shard_views(n_proj, world, rank, a.shard)
     my_n = len(mine)
     poses = pose_table(np.array([phi, alpha, beta]).T, xyz, geo.cor_shift)
     # "true" poses generate the measured data; the current estimate (half the jitter) is what fwd/grad use
@@ -377,7 +382,8 @@ def run_b200(a):
             # sees (POSIX shared memory, page-locked in each process); each rank moves only its 1/N over its own PCIe link
             sh_vol = SharedHostBuffer("tomo_b200_bench_vol", (n, n, n))
             sh_bp = SharedHostBuffer("tomo_b200_bench_bp", (n, n, n))
-            sh_proj = SharedHostBuffer("tomo_b200_bench_proj", (n_proj, n, n))
+            per_rank = (n_proj + world - 1) // world
+            sh_proj = SharedHostBuffer("tomo_b200_bench_proj", (world, per_rank, n, n))      # rank-major: block r = views of rank r
             if rank == 0:
                 sh_vol.tensor.copy_(h_vol)
             dist.barrier()
@@ -411,7 +417,7 @@ def run_b200(a):
                 be.sync_host()                                                  # the volume download (under the gradient kernel) has landed
                 return out
             dv = upload_volume()                                                # H2D volume: once per step, 1/N per rank
-            out_rows = sh_proj.tensor[mine[0]:mine[-1] + 1] if sharded_io else h_proj
+            out_rows = sh_proj.tensor[rank, :my_n] if sharded_io else h_proj
             be.forward_host(None, out_host=out_rows, vol_dev=dv)                # forward, D2H of this rank's views
             v = be.adjoint_host(h_meas, out_host=None, to_host=False)           # H2D projections, adjoint (device volume)
             if sharded_io:                                                      # reduce-scatter instead of the Allreduce of
@@ -473,7 +479,9 @@ def run_b200(a):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(a), "n_vox": int(n_vox), "n_proj": n_proj,
-                           "views_per_gpu": int(my_n), "parallelism": "views sharded x%d, volume replicated" % world,
+                           "views_per_gpu": int(my_n),
+                           "parallelism": "views sharded x%d (%s), volume replicated, backprojection all-reduced under the gradient kernel"
+                                          % (world, a.shard),
                            "l2": "inputs exceed L2 (volume %d MiB, projections %d MiB per rank)"
                                  % (4 * n ** 3 // 2 ** 20, 4 * my_n * n * n // 2 ** 20),
                            "phantom": "shepp3d", "poses": "examples/generate_data.py jitter, seed 20240229"},

@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -23,14 +24,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, shard="contiguous"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g, og = make_geoms(SHAPE, DSHAPE, N_PROJ, cor=np.array([[0.1 * i, 0, 0] for i in range(N_PROJ)]))
         phi, alpha, beta, xyz = random_poses(N_PROJ, 21)
-        sp = ShardedProjector(g, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz, backend_factory=OracleBackend)
+        sp = ShardedProjector(g, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz, backend_factory=OracleBackend, shard=shard)
         rng = np.random.default_rng(5)
         vol = rng.random(SHAPE).astype(np.float32)
         y = rng.random((N_PROJ, g.n_det)).astype(np.float32)
@@ -46,11 +47,12 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_rank_sharding_matches_single_process():
+@pytest.mark.parametrize("shard", ["contiguous", "interleaved"])
+def test_two_rank_sharding_matches_single_process(shard):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, shard), nprocs=world, join=True)
     g, og = make_geoms(SHAPE, DSHAPE, N_PROJ, cor=np.array([[0.1 * i, 0, 0] for i in range(N_PROJ)]))
     phi, alpha, beta, xyz = random_poses(N_PROJ, 21)
     rng = np.random.default_rng(5)
@@ -59,10 +61,14 @@ def test_two_rank_sharding_matches_single_process():
     meas = rng.random((N_PROJ, g.n_det)).astype(np.float32)
     op = O.OracleOperator(og, alpha=alpha, beta=beta, phi=phi, xyz_shift=xyz)
     ref_proj, ref_bp = op.forward(vol), op.adjoint(y)
-    # sharding follows np.array_split (sirt_mpi.py:40): rank 0 gets 3 views, rank 1 gets 2
-    assert list(out[0]["index"]) == [0, 1, 2] and list(out[1]["index"]) == [3, 4]
-    assert np.array_equal(np.concatenate([shard_views(N_PROJ, world, r) for r in range(world)]), np.arange(N_PROJ))
-    got_proj = np.concatenate([out[r]["proj"].reshape(len(out[r]["index"]), -1) for r in range(world)])
+    if shard == "contiguous":      # np.array_split (sirt_mpi.py:40): rank 0 gets 3 views, rank 1 gets 2
+        assert list(out[0]["index"]) == [0, 1, 2] and list(out[1]["index"]) == [3, 4]
+        assert np.array_equal(np.concatenate([shard_views(N_PROJ, world, r) for r in range(world)]), np.arange(N_PROJ))
+    else:                          # view i on rank i mod world: every rank sees the whole angular range
+        assert list(out[0]["index"]) == [0, 2, 4] and list(out[1]["index"]) == [1, 3]
+    got_proj = np.zeros((N_PROJ, g.n_det))
+    for r in range(world):
+        got_proj[out[r]["index"]] = out[r]["proj"].reshape(len(out[r]["index"]), -1)
     assert rel_l2(got_proj, ref_proj) < 1e-6
     for r in range(world):                      # all-reduced quantities are replicated
         assert rel_l2(out[r]["bp"], ref_bp) < 1e-6

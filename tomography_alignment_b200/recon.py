@@ -35,7 +35,7 @@ class _DeviceSolver(object):
         self.world = dist.get_world_size(group) if group is not None else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         check_world(self.n_proj, self.world)
-        self.my_index = shard_views(self.n_proj, self.world, self.rank)
+        self.my_index = shard_views(self.n_proj, self.world, self.rank, options['shard'] if 'shard' in options else "contiguous")
         self.my_n_proj = int(len(self.my_index))
         if backend is None:
             from .cuda_backend import CudaBackend
