@@ -8,10 +8,13 @@ projection-and-6-DOF-gradient pass over all views (SURVEY.md section 8d "s per a
 Shepp-Logan phantom with the jittered poses of examples/generate_data.py (seeded).  The unit of work is the
 voxel-ray update: n_vox * n_proj per operator, 3 operators per step.
 
-N > 1 (launched by torchrun, one rank per GPU): the views are sharded across ranks with
-np.array_split (recon/sirt_mpi.py:40), the volume is replicated, the backprojected volume is summed with an
-NCCL all-reduce and the per-view gradient table assembled with a zero-padded all-reduce; the total problem is
-fixed (strong scaling).
+N > 1 (launched by torchrun, one rank per GPU): the views are sharded across ranks (interleaved: view i on rank
+i mod N, so that every rank sees the whole angular range; --shard contiguous gives the np.array_split blocks of
+recon/sirt_mpi.py:40), the volume is replicated, the backprojected volume is summed with an NCCL all-reduce that is
+queued behind the backprojection and waited for after the gradient kernel, and the per-view gradient table is
+assembled with a zero-padded all-reduce; the total problem is fixed (strong scaling).  The end-to-end path keeps the
+volume, the backprojection and the projections in host buffers all ranks share (POSIX shared memory, page-locked):
+each rank moves its 1/N over its own PCIe link.
 
 Output: ONE JSON line on rank 0 (see the keys at the bottom).  `value` times device-resident inputs with CUDA
 events; `e2e` times the same three operators through the public ProjectionMatrix API with pinned HOST
