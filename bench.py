@@ -383,10 +383,11 @@ def run_b200(a):
         if sharded_io:
             # one box, one host memory: the volume, the backprojection and the projections live in host buffers every rank
             # sees (POSIX shared memory, page-locked in each process); each rank moves only its 1/N over its own PCIe link
-            sh_vol = SharedHostBuffer("tomo_b200_bench_vol", (n, n, n))
-            sh_bp = SharedHostBuffer("tomo_b200_bench_bp", (n, n, n))
+            job = "tomo_b200_bench_%s" % os.environ.get("MASTER_PORT", "0")      # one name per job on the box
+            sh_vol = SharedHostBuffer(job + "_vol", (n, n, n))
+            sh_bp = SharedHostBuffer(job + "_bp", (n, n, n))
             per_rank = (n_proj + world - 1) // world
-            sh_proj = SharedHostBuffer("tomo_b200_bench_proj", (world, per_rank, n, n))      # rank-major: block r = views of rank r
+            sh_proj = SharedHostBuffer(job + "_proj", (world, per_rank, n, n))      # rank-major: block r = views of rank r
             if rank == 0:
                 sh_vol.tensor.copy_(h_vol)
             dist.barrier()

@@ -652,6 +652,11 @@ def test_voxel_splat_deterministic_and_transpose(shape, dshape, kw):
     assert none is None and torch.equal(d_only, det)
     st = be.voxel_splat_adjoint(torch.as_tensor(y))
     assert rel_l2(st.cpu().numpy(), st_ref) <= TOL_PROJ
+    # the orphan backprojector (src/external_back_projection.f90) with origin = vox_origin - cor_shift is the same operator on the
+    # transposed detector image: two kernels (TMA-staged / plain gather vs splat transpose) and two Fortran routines agree
+    y_xz = torch.as_tensor(np.ascontiguousarray(y.transpose(0, 2, 1)))
+    vb = be.voxel_back(y_xz, origin=np.asarray(g.vox_origin) - np.asarray(g.cor_shift[0]))
+    assert rel_l2(vb.cpu().numpy(), st.cpu().numpy()) <= TOL_PROJ
     lhs = float((det.double().cpu() * torch.as_tensor(y).double()).sum())
     rhs = float((st.double().cpu().ravel() * torch.as_tensor(rec).double().ravel()).sum())
     assert abs(lhs - rhs) <= 1e-5 * abs(rhs)

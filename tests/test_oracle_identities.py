@@ -153,3 +153,21 @@ def test_orphan_forward_project_semantics():
     assert np.linalg.norm(orphan - live) / np.linalg.norm(live) < 5e-6
     _, og2 = make_geoms((12, 12, 12), (12, 12), 3, cor=[0.8, 0.0, 0.0])
     assert np.array_equal(O.forward_project_orphan(og2, rec, alpha, beta, phi, xyz), orphan)
+
+
+def test_voxel_back_projector_is_the_transposed_splat_matrix():
+    """Two independently restated Fortran routines must agree: back_project / voxel_back_bilinear
+    (src/external_back_projection.f90:30-68, a per-voxel gather of det_image(x', z')) with origin = vox_origin - cor_shift is
+    the transpose of the matrix bilinear_sparse emits (src/vox_wt_grad.f90:58-112, det index fx + ndim_x * fz) -- same transform
+    Ry(Rx Rz x + t), same four taps, same per-tap bounds checks -- once the detector image is transposed."""
+    from scipy import sparse
+    g, og = make_geoms((9, 8, 10), (11, 9), 3, cor=[0.3, 0.0, -0.2])
+    phi, alpha, beta, xyz = random_poses(3, 14, tilt=0.1, shift=2.5)
+    rng = np.random.default_rng(2)
+    y = rng.random((3, 11, 9))                                   # [view][x'][z'] as back_project reads it
+    for i in range(3):
+        orig = og.vox_origin - og.cor_shift[i]
+        back = O.voxel_back_project(og, y[i:i + 1], alpha[i:i + 1], beta[i:i + 1], phi[i:i + 1], xyz[i:i + 1], origin=orig)
+        dat, det, wts = O.voxel_forward_sparse(og, alpha[i], beta[i], phi[i], xyz[i], og.cor_shift[i])
+        S = sparse.coo_matrix((wts.astype(np.float64), (det, dat)), shape=(og.n_det, og.n_vox)).tocsr()
+        np.testing.assert_allclose(back, S.T @ y[i].T.ravel(), rtol=0, atol=2e-6)      # weights: float64 products vs float32 products

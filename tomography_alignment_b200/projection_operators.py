@@ -85,7 +85,8 @@ def reference_sample_counts(geometry, poses):
     first columns of the source / detector grids -- np.dot on (3,3)x(3,K) gives column 0 the same bits for
     every K >= 2 (tests/test_views_host.py checks this against the full-width evaluation) -- and handed to
     the C ABI in the pose record instead of being recomputed in C++."""
-    poses = np.asarray(poses, dtype=np.float64).reshape(-1, poses.shape[-1])
+    poses = np.asarray(poses, dtype=np.float64)
+    poses = poses.reshape(-1, poses.shape[-1])
     k = min(int(geometry.n_det), 4)
     org = np.asarray(geometry.vox_origin, dtype=np.float64)[:, np.newaxis]
     out = np.zeros((poses.shape[0], 2))
