@@ -158,3 +158,39 @@ def test_reference_alignment_functions_run_unchanged(ref):
     sol = af.gradient_descent(np.zeros(4), af.cost_xzab, af.gradient_xzab, args=(au, rec, angles[i], xyz[i], np.ones(4)),
                               options={"maxiter": 2})
     assert np.all(np.isfinite(np.asarray(sol[0] if isinstance(sol, tuple) else sol, dtype=float)))
+
+
+def test_reference_align_cc_consumes_the_operator_output(ref, monkeypatch):
+    """align/align_cc.py (BASELINE.json north_star lists it among the callers that must work unchanged) never touches the operators:
+    it cross-correlates consecutive projections.  Imported from the reference tree as it is (skimage, which the image lacks, is
+    stubbed: only cor_flipping / cross_correlation_skimage need it) and fed the (n_proj, nx, nz) projections the drop-in operator
+    produces: cross_correlation_numpy must recover integer detector shifts applied through xyz_shift."""
+    sk = types.ModuleType("skimage")
+    skr = types.ModuleType("skimage.registration")
+    skr.phase_cross_correlation = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("skimage is not installed"))
+    sk.registration = skr
+    monkeypatch.setitem(sys.modules, "skimage", sk)
+    monkeypatch.setitem(sys.modules, "skimage.registration", skr)
+    align = types.ModuleType("align")
+    align.__path__ = [os.path.join(REF, "align")]
+    monkeypatch.setitem(sys.modules, "align", align)
+    try:
+        cc = importlib.import_module("align.align_cc")
+        assert cc.__file__.startswith(REF)
+        n, n_proj = 16, 4
+        g, og = make_geoms((n, n, n), (n, n), n_proj)
+        x = np.zeros((n, n, n), np.float32)
+        x[5:11, 6:10, 4:12] = np.random.default_rng(0).random((6, 4, 8)).astype(np.float32) + 0.5
+        shifts = np.array([[0, 0, 0], [2, 0, 0], [2, 0, 0], [-1, 0, 0]], dtype=np.float64)        # whole detector pixels along x
+        pm = ref.ProjectionMatrix(g, precision=np.float32)
+        A = pm.projection_matrix(phi=np.zeros(n_proj), xyz_shift=shifts)                            # same angle, shifted object
+        from scipy import sparse
+        proj = sparse.csr_matrix.dot(A, x.ravel()).reshape(n_proj, n, n)
+        offsets, aligned = cc.cross_correlation_numpy(proj)
+        assert aligned.shape == proj.shape
+        # every projection is rolled back onto the first one: the step-to-step offsets are 2, 0, -3 pixels along x
+        assert offsets[:, 0].tolist() == [0.0, 2.0, 2.0, -1.0] and np.all(offsets[:, 1] == 0.0)
+        for i in range(1, n_proj):
+            assert np.abs(aligned[i] - aligned[0]).max() < 1e-3 * np.abs(proj[0]).max()
+    finally:
+        sys.modules.pop("align.align_cc", None)
