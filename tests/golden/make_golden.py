@@ -17,7 +17,11 @@ travels; tests/test_oracle_golden.py checks the oracle against it.
 Caveat: the numpy twins keep a sample only when all 8 corners are inside the
 volume, the live Fortran keeps every in-bounds corner.  The two agree exactly when the volume is zero
 on its outermost one-voxel shell (every in-bounds corner of a boundary sample lies on that shell), so
-the fixture volumes have a zero shell.
+the fixture volumes have a zero shell.  The Fortran's per-corner bounds checks themselves are pinned by a second
+evaluation of the SAME reference-authored twin on the problem padded by one voxel of zeros on every side (volume
+shape N + 2, ray points shifted by +1): there every sample that touches a real voxel has all 8 corners inside the
+padded array, so the twin keeps it with all its in-bounds corners -- exactly the live Fortran's result for a volume
+that is NOT zero on its shell ("*_full_padded" entries).
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -81,6 +85,21 @@ def main():
         A = np.zeros((geo.n_det, geo.n_vox))
         np.add.at(A, (det_inds, inds), wts)
         y = rng.random(geo.n_det)
+        # per-corner boundary semantics: the twin on the zero-padded problem (see the module docstring); own generator so that
+        # the entries above keep their values
+        rng2 = np.random.default_rng(sum(ord(c) for c in name))
+        rec_full = rng2.random(tuple(vshape))
+        y_full = rng2.random(geo.n_det)
+        pshape = vshape + 2
+        rec_pad = np.zeros(tuple(pshape))
+        rec_pad[1:-1, 1:-1, 1:-1] = rec_full
+        wts_p, det_p, inds_p, _ = rvu.ray_tracing_trilinear(pshape, p0 + 1.0, p1 + 1.0, geo.vox_ds, step, precision=np.float64)
+        Ap = np.zeros((geo.n_det, int(np.prod(pshape))))
+        np.add.at(Ap, (det_p, inds_p), wts_p)
+        out[name + "/rec_full"] = rec_full
+        out[name + "/y_full"] = y_full
+        out[name + "/A_dot_rec_full_padded"] = Ap.dot(rec_pad.ravel())
+        out[name + "/At_dot_y_full_padded"] = Ap.T.dot(y_full).reshape(tuple(pshape))[1:-1, 1:-1, 1:-1].ravel()
         vox_rot = vu.rigid_transformation(geo.vox_centers, alpha, beta, phi, xyz)
         vox_der = vu.derivative_rigid(geo.vox_centers, alpha, beta, phi, xyz)
         pre = name + "/"

@@ -203,6 +203,12 @@ def test_reference_numpy_golden_fixtures():
         shape = tuple(q("vox_shape"))
         at = be.adjoint(torch.as_tensor(q("y")[None, :].astype(np.float32))).cpu().numpy().reshape(shape)
         assert rel_l2(at[1:-1, 1:-1, 1:-1], q("At_dot_y").reshape(shape)[1:-1, 1:-1, 1:-1]) <= TOL_PROJ, name
+        # per-corner boundary semantics (volume non-zero on its shell): the reference's numpy twin on the zero-padded problem
+        full = be.forward(torch.as_tensor(q("rec_full").astype(np.float32)))[0].cpu().numpy()
+        assert rel_l2(full, q("A_dot_rec_full_padded")) <= TOL_PROJ, name
+        for gather in (False, True):
+            atf = be.adjoint(torch.as_tensor(q("y_full")[None, :].astype(np.float32)), gather=gather).cpu().numpy()
+            assert rel_l2(atf, q("At_dot_y_full_padded")) <= TOL_PROJ, (name, gather)
 
 
 def test_gpu_equals_cpu_emulation_of_the_same_cores():
