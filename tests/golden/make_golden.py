@@ -25,6 +25,7 @@ that is NOT zero on its shell ("*_full_padded" entries).
 
 Usage:  python tests/golden/make_golden.py
 """
+import copy
 import os
 import sys
 import types
@@ -100,6 +101,13 @@ def main():
         out[name + "/y_full"] = y_full
         out[name + "/A_dot_rec_full_padded"] = Ap.dot(rec_pad.ravel())
         out[name + "/At_dot_y_full_padded"] = Ap.T.dot(y_full).reshape(tuple(pshape))[1:-1, 1:-1, 1:-1].ravel()
+        # the gradient twin on the same padded problem: it reads only vox_shape off the geometry for the bounds/indices, the pose
+        # derivative tables do not depend on the volume's extent
+        geo_p = copy.copy(geo)
+        geo_p.vox_shape = pshape
+        proj_p, grad_p = rvu.ray_weights_der(p0 + 1.0, p1 + 1.0, geo_p, (phi, alpha, beta), xyz, rec_pad)
+        out[name + "/proj_full_padded"] = proj_p
+        out[name + "/grad_full_padded"] = grad_p
         vox_rot = vu.rigid_transformation(geo.vox_centers, alpha, beta, phi, xyz)
         vox_der = vu.derivative_rigid(geo.vox_centers, alpha, beta, phi, xyz)
         pre = name + "/"

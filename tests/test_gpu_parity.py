@@ -209,6 +209,9 @@ def test_reference_numpy_golden_fixtures():
         for gather in (False, True):
             atf = be.adjoint(torch.as_tensor(q("y_full")[None, :].astype(np.float32)), gather=gather).cpu().numpy()
             assert rel_l2(atf, q("At_dot_y_full_padded")) <= TOL_PROJ, (name, gather)
+        outf = be.proj_grad(torch.as_tensor(q("rec_full").astype(np.float32)))
+        assert rel_l2(outf["proj"][0].cpu().numpy(), q("proj_full_padded")) <= TOL_PROJ, name
+        assert rel_l2(outf["dproj"][0].cpu().numpy(), q("grad_full_padded")) <= TOL_GRAD, name
 
 
 def test_gpu_equals_cpu_emulation_of_the_same_cores():
