@@ -365,8 +365,10 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                         float* const se = (float*)__cvta_shared_to_generic(act ? sb : ((sb & 0x7cu) | dummy_b));
                         rmw4<O10, O01, O11>(se, wy0, wy1, wz0);
                         __syncwarp();
+#ifndef TOMO_PROBE_HALF_RMW          // timing probe only: drops the z-ceil plane
                         rmw4<O10, O01, O11>(se + OZ, wy0, wy1, f2);
                         __syncwarp();
+#endif
                     } else {
                         // rare (W_z < 1 makes two adjacent lanes share a z cell ~ once per 1/(1-W_z) samples):
                         // lanes flagged dup go in a second pass

@@ -150,6 +150,22 @@ TOMO_HD f2 f2_sub(f2 b, f2 a)
 // The 8 zero-padded corner loads and the trilinear interpolant in nested-lerp form, the two x-corners of each
 // (y, z) corner packed in one register pair (.x = m-floor x, .y = m-ceil x).  Leaves behind the pieces the
 // spatial gradient is built from: dzA/dzB (z differences at y-floor / y-ceil), dy (y differences), gx, val.
+#if defined(TOMO_PROBE_LDG64) && defined(__CUDA_ARCH__)
+// TIMING PROBE ONLY (wrong values for odd offsets): the z pair of every (x, y) corner as one aligned 64-bit load,
+// lerps ordered x, y, z so that the packed pairs are the z pairs.
+#define RAY_SAMPLE(c, fx_, fy2_, fz2_)                                                                \
+    const float2* cq = (const float2*)((unsigned long long)(c) & ~7ull);                               \
+    const float2 q00 = __ldg(cq), q10 = __ldg((const float2*)((const float*)cq + o10));                 \
+    const float2 q01 = __ldg((const float2*)((const float*)cq + o01)), q11 = __ldg((const float2*)((const float*)cq + o11)); \
+    const f2 fx2_ = f2_make(fx_, fx_);                                                                  \
+    const f2 v00 = f2_make(q00.x, q00.y), v10 = f2_make(q10.x, q10.y), v01 = f2_make(q01.x, q01.y), v11 = f2_make(q11.x, q11.y); \
+    const f2 dzA = f2_sub(v10, v00), dzB = f2_sub(v11, v01);                                            \
+    const f2 aA = f2_fma(fx2_, dzA, v00), aB = f2_fma(fx2_, dzB, v01);                                  \
+    const f2 dy = f2_sub(aB, aA);                                                                       \
+    const f2 b = f2_fma(fy2_, dy, aA);                                                                  \
+    const float gx = b.y - b.x;                                                                         \
+    const float val = fmaf((fz2_).x, gx, b.x);
+#else
 #define RAY_SAMPLE(c, fx_, fy2_, fz2_)                                                                \
     const f2 loA = f2_make(TOMO_LDG(c),            TOMO_LDG(c + o10));                                  \
     const f2 hiA = f2_make(TOMO_LDG(c + oz),       TOMO_LDG(c + o10 + oz));                             \
@@ -161,6 +177,7 @@ TOMO_HD f2 f2_sub(f2 b, f2 a)
     const f2 b = f2_fma(fy2_, dy, aA);                                                                  \
     const float gx = b.y - b.x;                                                                         \
     const float val = fmaf(fx_, gx, b.x);
+#endif
 
 // Forward only: (cell offset, float32 fraction) marching, re-based from float64 every RAY_REBASE
 // samples.  The interpolant is continuous, so a cell decision that is off by float32 rounding next
