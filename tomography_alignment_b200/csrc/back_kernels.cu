@@ -296,7 +296,7 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
     constexpr int STX = SGX * TSY * TSZ, STY = SGY * TSZ, STZ = SGZ;
     constexpr int O01 = STY, O10 = STX, O11 = STX + STY, OZ = STZ;
     const float hi[3] = {(float)(TOMO_BT_X + 1), (float)(TOMO_BT_Y + 1), (float)(TOMO_BT_Z + 1)};
-    const int stepoff = tv.di_step, stepx = tv.di_step + STX;
+    const unsigned stepoff4 = 4u * (unsigned)tv.di_step;        // byte step of the integer part of |D| (0 for steps below one voxel)
     // Dummy cells: a lane with nothing to add is redirected to (its own bank) + DUMMY, so it stays conflict-free
     // against the active lanes.  The eight corner offsets span [OMIN, OMIN + TGUARD - 1]; with DUMMY = -OMIN
     // rounded up to a multiple of 32 every dummy access falls into the front guard or the x = 0 ghost plane of the
@@ -385,11 +385,10 @@ __device__ __forceinline__ void tile_march_view(float* __restrict__ acc, const T
                     // advance one sample: one-sided carries, the strides folded into one address increment
                     ++k;
                     f0 += df0; f1 += df1; f2 += df2;
-                    int inc = stepoff;
-                    if (f0 >= 1.0f) { f0 -= 1.0f; inc = stepx; }
-                    if (f1 >= 1.0f) { f1 -= 1.0f; inc += STY; }
-                    if (f2 >= 1.0f) { f2 -= 1.0f; inc += STZ; }
-                    sb += 4u * (unsigned)inc;
+                    sb += stepoff4;
+                    if (f0 >= 1.0f) { f0 -= 1.0f; sb += 4u * (unsigned)STX; }
+                    if (f1 >= 1.0f) { f1 -= 1.0f; sb += 4u * (unsigned)STY; }
+                    if (f2 >= 1.0f) { f2 -= 1.0f; sb += 4u * (unsigned)STZ; }
                 }
             }
         }
