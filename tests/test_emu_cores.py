@@ -70,6 +70,32 @@ def test_projection_gradient(shape, dshape, n_proj, kw):
         assert abs(out["cost"][i].item() - 0.5 * res @ res) <= 1e-5 * (0.5 * res @ res)
 
 
+def test_compile_time_stride_variants_all_sign_octants():
+    """64^3 is one of the cubes whose padded strides are template constants in ray_core.h (ray_march_fixed): eight variants, one
+    per sign octant of the step D.  phi picks the signs of D_x, D_y, the tilt that of D_z; both marches against the oracle."""
+    n = 64
+    phis = np.array([0.3, 0.3, 1.9, 1.9, 3.5, 3.5, 5.2, 5.2])
+    alpha = np.array([0.03, -0.03] * 4)
+    beta = np.array([-0.02, 0.025] * 4)
+    xyz = np.random.default_rng(5).uniform(-2, 2, (8, 3))
+    g, og = make_geoms((n, n, n), (n, n), 8)
+    be = EmuBackend(g)
+    be.set_poses(pose_table(np.array([phis, alpha, beta]).T, xyz, g.cor_shift))
+    vol = np.random.default_rng(6).random((n, n, n)).astype(np.float32)
+    out = be.proj_grad(vol)
+    octants = set()
+    for i in range(8):
+        p, gr = O.forward_proj_grad(og, alpha[i], beta[i], phis[i], xyz[i], og.cor_shift[i], vol)
+        assert rel_l2(out["proj"][i].numpy(), p) <= TOL_PROJ
+        assert rel_l2(out["dproj"][i].numpy(), gr) <= TOL_GRAD
+        vs = O.ViewSetup(og, alpha[i], beta[i], phis[i], xyz[i], og.cor_shift[i])
+        d = vs.r_hat[:, 0]
+        octants.add(tuple(np.sign(d).astype(int)))
+    assert len(octants) == 8, octants
+    fwd = be.forward(vol).numpy().reshape(8, -1)
+    assert rel_l2(fwd, out["proj"].numpy().reshape(8, -1)) <= 2e-6          # float32 march vs fixed-point march
+
+
 @pytest.mark.parametrize("shape,dshape,n_proj,kw", CASES[:3])
 def test_voxel_driven_bilinear_backprojector(shape, dshape, n_proj, kw):
     g, og, be, op, (phi, alpha, beta, xyz) = setup(shape, dshape, n_proj, **kw)

@@ -182,7 +182,10 @@ TOMO_HD f2 f2_sub(f2 b, f2 a)
 // Forward only: (cell offset, float32 fraction) marching, re-based from float64 every RAY_REBASE
 // samples.  The interpolant is continuous, so a cell decision that is off by float32 rounding next
 // to a lattice plane changes nothing.
-template <int SGZ>
+// SXP / SYP != 0: the padded strides (and with SGX / SGY the signed corner offsets) are compile-time constants, so all eight
+// corner loads address off ONE 64-bit register with immediate offsets (otherwise every corner costs a 64-bit add: 6 of the
+// ~42 instructions of a sample).  SXP = SYP = 0: strides and signs at run time (SGX, SGY unused).
+template <int SGX, int SGY, int SGZ, int SXP, int SYP>
 TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
                                int ix, int iz, RaySums& out)
 {
@@ -193,7 +196,7 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
 #pragma unroll
     for (int a = 0; a < 3; ++a) { const double ad = fabs(r.D[a]); df[a] = (float)(ad - floor(ad)); }
     // the z stride (+-1) is a template constant: the z-ceil corner of each pair is an immediate offset
-    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1];
+    const int o10 = SXP ? SGX * SXP : r.st[0], o01 = SYP ? SGY * SYP : r.st[1], o11 = o10 + o01;
     constexpr int oz = SGZ;
     float acc = 0.f;
     for (int jc = r.j0; jc < r.j1; jc += RAY_REBASE) {
@@ -204,7 +207,7 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
             double fr;
             ray_cell(r, a, jc, ust[a], off, fr);
             f[a] = (float)fr;
-            if (f[a] >= 1.0f) { f[a] -= 1.0f; off += r.st[a]; }
+            if (f[a] >= 1.0f) { f[a] -= 1.0f; off += (a == 0) ? o10 : (a == 1) ? o01 : oz; }
         }
         const int jend = (jc + RAY_REBASE < r.j1) ? jc + RAY_REBASE : r.j1;
 #pragma unroll 2
@@ -214,9 +217,9 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
             acc += val;
             f[0] += df[0]; f[1] += df[1]; f[2] += df[2];
             off += r.stepoff;
-            if (f[0] >= 1.0f) { f[0] -= 1.0f; off += r.st[0]; }
-            if (f[1] >= 1.0f) { f[1] -= 1.0f; off += r.st[1]; }
-            if (f[2] >= 1.0f) { f[2] -= 1.0f; off += SGZ; }
+            if (f[0] >= 1.0f) { f[0] -= 1.0f; off += o10; }
+            if (f[1] >= 1.0f) { f[1] -= 1.0f; off += o01; }
+            if (f[2] >= 1.0f) { f[2] -= 1.0f; off += oz; }
         }
     }
     out.acc = acc;
@@ -226,14 +229,14 @@ TOMO_HD void ray_march_forward(const float* __restrict__ vol, const double* __re
 // lattice planes (one-sided differences, src/ray_wt_grad.f90:142-220), so the cell of every sample
 // must be the float64 one: the fraction is carried as 64-bit fixed point, which accumulates j*D
 // exactly (no re-basing, no branches); only the interpolation weights are rounded to float32.
-template <int SGZ>
+template <int SGX, int SGY, int SGZ, int SXP, int SYP>
 TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
                                 int ix, int iz, RaySums& out)
 {
     RaySetup r;
     ray_setup(V, dm, ix, iz, r);
     const int ust[3] = {dm.sxp, dm.syp, 1};
-    const int o01 = r.st[1], o10 = r.st[0], o11 = r.st[0] + r.st[1];
+    const int o10 = SXP ? SGX * SXP : r.st[0], o01 = SYP ? SGY * SYP : r.st[1], o11 = o10 + o01;
     constexpr int oz = SGZ;
     unsigned fh[3], fl[3], dh[3], dl[3];
     int off = 0;
@@ -249,8 +252,9 @@ TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __r
     }
     float acc = 0.f, s0z = 0.f, s1z = 0.f;
     f2 s0xy = f2_make(0.f, 0.f), s1xy = f2_make(0.f, 0.f);
-    float fj = (float)r.j0;
-    for (int j = r.j0; j < r.j1; ++j) {
+    // the sample index is needed as a float only (moment weights): it is also the loop counter (exact below 2^24)
+    const float fjend = (float)r.j1;
+    for (float fj = (float)r.j0; fj < fjend; fj += 1.0f) {
         const float fx = fix_to_float(fh[0]), fy = fix_to_float(fh[1]), fz = fix_to_float(fh[2]);
         const float* __restrict__ c = vol + off;
         const f2 fy2 = f2_make(fy, fy);
@@ -263,25 +267,61 @@ TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __r
         const f2 gxy = f2_make(gx, gy);
         s0xy = f2_fma(gxy, f2_make(1.f, 1.f), s0xy); s0z += gz;
         s1xy = f2_fma(f2_make(fj, fj), gxy, s1xy); s1z = fmaf(fj, gz, s1z);
-        fj += 1.0f;
         off += r.stepoff;
-        off += (int)fix64_add(fh[0], fl[0], dh[0], dl[0]) * r.st[0];
-        off += (int)fix64_add(fh[1], fl[1], dh[1], dl[1]) * r.st[1];
-        off += (int)fix64_add(fh[2], fl[2], dh[2], dl[2]) * SGZ;
+        if (fix64_add(fh[0], fl[0], dh[0], dl[0])) off += o10;
+        if (fix64_add(fh[1], fl[1], dh[1], dl[1])) off += o01;
+        if (fix64_add(fh[2], fl[2], dh[2], dl[2])) off += oz;
     }
     out.acc = acc;
     out.s0[0] = s0xy.x * (float)r.sg[0]; out.s0[1] = s0xy.y * (float)r.sg[1]; out.s0[2] = s0z * (float)r.sg[2];
     out.s1[0] = s1xy.x * (float)r.sg[0]; out.s1[1] = s1xy.y * (float)r.sg[1]; out.s1[2] = s1z * (float)r.sg[2];
 }
 
+template <bool GRAD, int SGX, int SGY, int SGZ, int SXP, int SYP>
+TOMO_HD void ray_march_one(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                           int ix, int iz, RaySums& out)
+{
+    if (GRAD) ray_march_gradient<SGX, SGY, SGZ, SXP, SYP>(vol, V, dm, ix, iz, out);
+    else      ray_march_forward<SGX, SGY, SGZ, SXP, SYP>(vol, V, dm, ix, iz, out);
+}
+
+// Signs of the step D: uniform per view, so these branches never diverge.
+template <bool GRAD, int SXP, int SYP>
+TOMO_HD void ray_march_fixed(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
+                             int ix, int iz, RaySums& out)
+{
+    const int sg = (V[V_D + 0] < 0.0 ? 4 : 0) | (V[V_D + 1] < 0.0 ? 2 : 0) | (V[V_D + 2] < 0.0 ? 1 : 0);
+    switch (sg) {
+        case 0:  ray_march_one<GRAD,  1,  1,  1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        case 1:  ray_march_one<GRAD,  1,  1, -1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        case 2:  ray_march_one<GRAD,  1, -1,  1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        case 3:  ray_march_one<GRAD,  1, -1, -1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        case 4:  ray_march_one<GRAD, -1,  1,  1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        case 5:  ray_march_one<GRAD, -1,  1, -1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        case 6:  ray_march_one<GRAD, -1, -1,  1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+        default: ray_march_one<GRAD, -1, -1, -1, SXP, SYP>(vol, V, dm, ix, iz, out); break;
+    }
+}
+
+// Padded strides of an N^3 volume: syp = tomo_nzp(N), sxp = (N + 2 TOMO_PAD) * syp.  The cubes of BASELINE.json's configurations
+// (and 128^3) get the compile-time-stride variants; every other shape takes the run-time-stride march.  Same arithmetic, same bits.
+#define RAY_CUBE_SYP(N) ((((N) + 2 * TOMO_PAD + 31) / 32) * 32)
+#define RAY_CUBE_SXP(N) (((N) + 2 * TOMO_PAD) * RAY_CUBE_SYP(N))
 template <bool GRAD>
 TOMO_HD void ray_march(const float* __restrict__ vol, const double* __restrict__ V, const RayDims dm,
                        int ix, int iz, RaySums& out)
 {
-    // sign of the z step: uniform per view, so this branch never diverges
-    const bool zneg = V[V_D + 2] < 0.0;
-    if (GRAD) { if (zneg) ray_march_gradient<-1>(vol, V, dm, ix, iz, out); else ray_march_gradient<1>(vol, V, dm, ix, iz, out); }
-    else      { if (zneg) ray_march_forward<-1>(vol, V, dm, ix, iz, out);  else ray_march_forward<1>(vol, V, dm, ix, iz, out); }
+#ifndef RAY_NO_FIXED_STRIDES
+#define RAY_TRY_CUBE(N)                                                                                  \
+    if (dm.syp == RAY_CUBE_SYP(N) && dm.sxp == RAY_CUBE_SXP(N)) {                                        \
+        ray_march_fixed<GRAD, RAY_CUBE_SXP(N), RAY_CUBE_SYP(N)>(vol, V, dm, ix, iz, out);                \
+        return;                                                                                          \
+    }
+    RAY_TRY_CUBE(512) RAY_TRY_CUBE(256) RAY_TRY_CUBE(1024) RAY_TRY_CUBE(128) RAY_TRY_CUBE(64)
+#undef RAY_TRY_CUBE
+#endif
+    if (V[V_D + 2] < 0.0) ray_march_one<GRAD, 1, 1, -1, 0, 0>(vol, V, dm, ix, iz, out);
+    else                  ray_march_one<GRAD, 1, 1,  1, 0, 0>(vol, V, dm, ix, iz, out);
 }
 
 // d proj / d theta_k for one ray, API order [tx, ty, tz, phi, alpha, beta]
