@@ -29,6 +29,9 @@
 #define TOMO_LDG(p) (*(p))
 #endif
 
+#ifndef RAY_GRAD_UNROLL
+#define RAY_GRAD_UNROLL 1
+#endif
 #ifndef RAY_REBASE
 #define RAY_REBASE 64
 #endif
@@ -254,6 +257,8 @@ TOMO_HD void ray_march_gradient(const float* __restrict__ vol, const double* __r
     f2 s0xy = f2_make(0.f, 0.f), s1xy = f2_make(0.f, 0.f);
     // the sample index is needed as a float only (moment weights): it is also the loop counter (exact below 2^24)
     const float fjend = (float)r.j1;
+    constexpr int kUnroll = RAY_GRAD_UNROLL;
+#pragma unroll kUnroll
     for (float fj = (float)r.j0; fj < fjend; fj += 1.0f) {
         const float fx = fix_to_float(fh[0]), fy = fix_to_float(fh[1]), fz = fix_to_float(fh[2]);
         const float* __restrict__ c = vol + off;

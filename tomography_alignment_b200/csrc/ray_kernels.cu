@@ -119,9 +119,17 @@ __device__ __forceinline__ void ray_kernel_body(const RayArgs& A)
 }
 
 // Measured on B200 (profiles/README.md): the forward march is fastest at 48 registers (5 blocks/SM) with the
-// sample loop unrolled twice; the gradient march is insensitive to both and keeps ptxas' own budget.
-__global__ void __launch_bounds__(TILE_Z * TILE_X, 40 / TILE_X) ray_kernel_forward(const RayArgs A) { ray_kernel_body<false>(A); }
-__global__ void __launch_bounds__(TILE_Z * TILE_X) ray_kernel_gradient(const RayArgs A) { ray_kernel_body<true>(A); }
+// sample loop unrolled twice (6 blocks / 40 registers: -0.6 %, 4 blocks: +0.4 %).
+#ifndef RAY_FWD_MINB
+#define RAY_FWD_MINB (40 / TILE_X)
+#endif
+__global__ void __launch_bounds__(TILE_Z * TILE_X, RAY_FWD_MINB) ray_kernel_forward(const RayArgs A) { ray_kernel_body<false>(A); }
+// gradient: 5 blocks per SM (48 registers, a few spills outside the sample loop) beat ptxas' own 52 registers / 4 blocks by 6.6 %
+// once the compile-time strides had shortened the loop (long-scoreboard stalls dominate it): 48.4 -> 45.2 ms per 180 views
+#ifndef RAY_GRAD_MINB
+#define RAY_GRAD_MINB 5
+#endif
+__global__ void __launch_bounds__(TILE_Z * TILE_X, RAY_GRAD_MINB) ray_kernel_gradient(const RayArgs A) { ray_kernel_body<true>(A); }
 
 // ---- z-quad kernels (zq_core.h): a thread owns four z-adjacent rays -------------------------------------------------
 // Block = 8 warps; a warp covers 4 detector columns x 32 rows (8 lanes of 4 rays per column), a block 32 columns x 32 rows.
