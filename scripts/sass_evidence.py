@@ -14,7 +14,7 @@ for ln in sass.splitlines():
     m = re.search(r"Function : (\S+)", ln)
     if m:
         cur = m.group(1); funcs[cur] = []
-    elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+    elif cur and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", ln):
         funcs[cur].append(re.sub(r"/\* 0x[0-9a-f]+ \*/", "", ln).rstrip())
 
 
@@ -25,7 +25,7 @@ def opcode(ln):
 
 def loops(lines):
     """(start, end) of backward branches: innermost loops."""
-    addr = {int(re.search(r"/\*([0-9a-f]{4})\*/", l).group(1), 16): i for i, l in enumerate(lines)}
+    addr = {int(re.search(r"/\*([0-9a-f]{4,6})\*/", l).group(1), 16): i for i, l in enumerate(lines)}
     out = []
     for i, l in enumerate(lines):
         m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s+)?0x([0-9a-f]+)", l)
