@@ -25,7 +25,7 @@
 //         ceil plane is lane l+1's floor plane).
 //     The inner loop is branch-free: a lane outside its sample range is redirected to dummy cells in its
 //     own bank (guard / ghost area) instead of being predicated off, and the corner pairs go through
-//     packed fp32x2 FMAs -- 52 SASS instructions per warp-sample (16 of them the LDS/STS of the 8 RMWs).
+//     packed fp32x2 FMAs -- 51 SASS instructions per warp-sample (16 of them the LDS/STS of the 8 RMWs).
 //     A sample is handled by every tile that owns one of its corner voxels; contributions that land
 //     on the tile's ghost cells are dropped (the neighbouring tile adds them), so each voxel sums
 //     exactly the reference's terms, in a fixed order: results are bitwise reproducible.
