@@ -98,9 +98,11 @@ TOMO_API int tomo_views_kinds(const double* views_host, int n_proj);
 
 /* ---- padded volume -------------------------------------------------------------------------- */
 /* The ray-driven kernels read a zero-bordered copy of the volume (zero-padded-corner semantics of
- * src/ray_wt_grad.f90:35-89 without per-corner branches): [nx+2P][ny+2P][nzp], nzp = nz+2P rounded
- * up to 32 floats, data at offset (P,P,P), P = TOMO_PAD; the buffer holds 32 floats of zero slack before and after it
- * (tomo_padded_volume_bytes() includes them, tomo_pad_volume writes them). */
+ * src/ray_wt_grad.f90:35-89 without per-corner branches): [nx+2P][nyp][syp], data at offset (P,P,P), P = TOMO_PAD, with
+ * nyp >= ny+2P rows per plane and syp >= nz+2P (a multiple of 32) floats per row -- the pitches are the library's choice
+ * (those of the next cube of 64^3 ... 1024^3 when that costs at most twice the memory: the ray kernels have compile-time-stride
+ * variants for them); callers only size the buffer with tomo_padded_volume_bytes() and fill it with tomo_pad_volume().  The
+ * buffer holds 32 floats of zero slack before and after the volume (included in the byte count, written by tomo_pad_volume). */
 TOMO_API size_t tomo_padded_volume_bytes(const TomoGeom* geom);
 TOMO_API int tomo_pad_volume(const TomoGeom* geom, const float* vol_dev, float* volpad_dev, void* stream);
 

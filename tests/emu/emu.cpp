@@ -13,7 +13,9 @@
 
 EMU_API void emu_pad(const TomoGeom* g, const float* vol, float* pad)
 {
-    const int nyp = g->ny + 2 * TOMO_PAD, nzp = tomo_nzp(g->nz), nxp = g->nx + 2 * TOMO_PAD;
+    int nyp, nzp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &nzp);
+    const int nxp = g->nx + 2 * TOMO_PAD;
     for (size_t i = 0; i < (size_t)nxp * nyp * nzp + TOMO_PAD_HEAD + TOMO_PAD_TAIL; ++i) pad[i] = 0.f;
     pad += TOMO_PAD_HEAD;                                  // buffer layout of tomo_pad_volume: head slack, volume, tail slack
     for (int x = 0; x < g->nx; ++x) for (int y = 0; y < g->ny; ++y) for (int z = 0; z < g->nz; ++z)
@@ -28,7 +30,9 @@ EMU_API void emu_proj_grad(const TomoGeom* g, const double* views, int n_proj, c
                            const float* meas, float* proj, float* dproj, double* grad6, double* cost, int want_grad)
 {
     const float* volpad = volpad_buf + TOMO_PAD_HEAD;
-    const RayDims dm = {g->nx, g->ny, g->nz, (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz), tomo_nzp(g->nz)};
+    int nyp_, syp_;
+    tomo_pad_pitch(g->ny, g->nz, &nyp_, &syp_);
+    const RayDims dm = {g->nx, g->ny, g->nz, nyp_ * syp_, syp_};
     const size_t n_det = (size_t)g->ndx * g->ndz;
     for (int v = 0; v < n_proj; ++v) {
         const double* V = views + (size_t)v * TOMO_VIEW_STRIDE;

@@ -22,6 +22,7 @@ CASES = [
     ((12, 12, 12), (12, 12), 3, dict(shift=14.0, phis=[0.2, 1.1, 2.0])),   # rays mostly / entirely miss the volume
     ((5, 40, 3), (5, 3), 3, dict()),                                   # ragged: tiny x/z, long y
     ((33, 9, 35), (33, 35), 2, dict(phis=[0.4, 2.9])),                 # not a multiple of the 32x8 tile
+    ((20, 56, 60), (20, 60), 4, dict(phis=[0.3, 1.9, 3.5, 5.2])),      # not a cube, but laid out with the pitches of 64^3 (tomo_pad_pitch)
 ]
 
 
@@ -105,7 +106,8 @@ def test_voxel_driven_bilinear_backprojector(shape, dshape, n_proj, kw):
 
 
 @pytest.mark.parametrize("shape,dshape,kw", [((16, 16, 16), (16, 16), dict()), ((14, 20, 37), (14, 37), dict(cor=[0.4, 0, 0])),
-                                              ((12, 12, 12), (18, 9), dict(shift=6.0)), ((16, 16, 16), (16, 16), dict(step=0.5))])
+                                              ((12, 12, 12), (18, 9), dict(shift=6.0)), ((16, 16, 16), (16, 16), dict(step=0.5)),
+                                              ((20, 56, 60), (20, 60), dict())])       # pitches of 64^3, 64 planes to visit
 def test_separable_forward_for_untilted_views(shape, dshape, kw):
     """alpha = beta = 0 (the API's default poses): the separable cores of sep_core.h reproduce the oracle."""
     n_proj = 7

@@ -27,6 +27,7 @@ CASES = [
     ((5, 40, 3), (5, 3), 3, dict()),
     ((33, 9, 35), (33, 35), 2, dict(phis=[0.4, 2.9])),
     ((40, 40, 40), (40, 40), 1, dict(phis=[0.77])),                       # n_proj == 1
+    ((20, 56, 60), (20, 60), 4, dict(phis=[0.3, 1.9, 3.5, 5.2])),         # not a cube, laid out with the pitches of 64^3 (tomo_pad_pitch)
 ]
 
 
@@ -448,7 +449,8 @@ def test_batched_alignment_recovers_jitter_on_gpu():
 
 @pytest.mark.parametrize("shape,dshape,kw", [((16, 16, 16), (16, 16), dict()), ((14, 20, 37), (14, 37), dict(cor=[0.4, 0, 0])),
                                               ((12, 12, 12), (18, 9), dict(shift=6.0)), ((40, 40, 300), (40, 300), dict()),
-                                              ((16, 16, 16), (16, 16), dict(step=0.5))])
+                                              ((16, 16, 16), (16, 16), dict(step=0.5)),
+                                              ((20, 56, 60), (20, 60), dict())])       # pitches of 64^3, 64 planes to visit
 def test_separable_forward_for_untilted_views(shape, dshape, kw):
     """alpha = beta = 0 (the default poses of projection_matrix): sep_forward_kernel, incl. volumes taller than one
     z chunk (300 planes = 3 chunks) and a table that mixes tilted and untilted views."""

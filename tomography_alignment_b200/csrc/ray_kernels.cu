@@ -278,7 +278,9 @@ int tomo_grad_separable_launch(const TomoGeom* g, const void* views, int n_proj,
 
 static int check_sizes(const TomoGeom* g)
 {
-    const double padded = (double)(g->nx + 2 * TOMO_PAD) * (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz);
+    int nyp, syp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &syp);
+    const double padded = (double)(g->nx + 2 * TOMO_PAD) * nyp * syp;
     if (padded >= 2147483647.0) { tomo_set_error("padded volume exceeds 2^31 elements (32-bit kernel offsets)"); return TOMO_E_RANGE; }
     return 0;
 }
@@ -286,7 +288,9 @@ static int check_sizes(const TomoGeom* g)
 extern "C" size_t tomo_padded_volume_bytes(const TomoGeom* g)
 {
     if (!g) return 0;
-    return sizeof(float) * ((size_t)(g->nx + 2 * TOMO_PAD) * (g->ny + 2 * TOMO_PAD) * tomo_nzp(g->nz) + TOMO_PAD_HEAD + TOMO_PAD_TAIL);
+    int nyp, syp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &syp);
+    return sizeof(float) * ((size_t)(g->nx + 2 * TOMO_PAD) * nyp * syp + TOMO_PAD_HEAD + TOMO_PAD_TAIL);
 }
 
 extern "C" int tomo_pad_volume(const TomoGeom* g, const float* vol, float* pad, void* stream)
@@ -296,8 +300,9 @@ extern "C" int tomo_pad_volume(const TomoGeom* g, const float* vol, float* pad, 
     const size_t total = tomo_padded_volume_bytes(g) / sizeof(float);
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads > 148 * 64 ? 148 * 64 : (total + threads - 1) / threads);
-    pad_volume_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(vol, pad, g->nx, g->ny, g->nz,
-                                                                     g->ny + 2 * TOMO_PAD, tomo_nzp(g->nz));
+    int nyp, syp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &syp);
+    pad_volume_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(vol, pad, g->nx, g->ny, g->nz, nyp, syp);
     return tomo_check_cuda(cudaGetLastError(), "pad_volume_kernel");
 }
 
@@ -308,8 +313,9 @@ static int fill_args(const TomoGeom* g, const void* views, int n_proj, const flo
     A->volpad = volpad + TOMO_PAD_HEAD; A->views = (const double*)views;      // the padded volume proper starts behind the head slack
     A->meas = nullptr; A->proj = nullptr; A->dproj = nullptr; A->partial = nullptr; A->skip_separable = 0; A->skip_zq = 0;
     A->nx = g->nx; A->ny = g->ny; A->nz = g->nz; A->ndx = g->ndx; A->ndz = g->ndz; A->n_proj = n_proj;
-    A->syp = tomo_nzp(g->nz);
-    A->sxp = (g->ny + 2 * TOMO_PAD) * A->syp;
+    int nyp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &A->syp);
+    A->sxp = nyp * A->syp;
     A->nxt = (g->ndx + TILE_X - 1) / TILE_X;
     A->nzt = (g->ndz + TILE_Z - 1) / TILE_Z;
     // bands of about RAY_BAND_TILES x-tiles: 16 tiles = 128 detector columns keep a band of a 36-plane slab of a 512^2

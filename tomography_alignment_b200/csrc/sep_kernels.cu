@@ -281,9 +281,10 @@ int tomo_forward_separable_launch(const TomoGeom* g, const void* views, int n_pr
     SepArgs A;
     A.volpad = volpad + TOMO_PAD_HEAD; A.views = (const double*)views; A.proj = proj;
     A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
-    A.nzp = tomo_nzp(g->nz);
-    A.syp = A.nzp;
-    A.sxp = (g->ny + 2 * TOMO_PAD) * A.syp;
+    A.nzp = tomo_nzp(g->nz);                       // planes to visit; the pitches may be those of the next cube (tomo_pad_pitch)
+    int nyp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &A.syp);
+    A.sxp = nyp * A.syp;
     A.nxt = (g->ndx + SEP_WARPS - 1) / SEP_WARPS;
     A.nchunk = (A.nzp - 1 + SEP_OUT - 1) / SEP_OUT;
     // the last chunk must be able to serve floor planes up to nzp - 2 from SEP_CHUNK staged planes
@@ -338,9 +339,10 @@ int tomo_grad_separable_launch(const TomoGeom* g, const void* views, int n_proj,
     SepGradArgs A;
     A.volpad = volpad + TOMO_PAD_HEAD; A.views = (const double*)views; A.meas = meas; A.proj = proj; A.dproj = dproj; A.partial = partial;
     A.nx = g->nx; A.ny = g->ny; A.nz = g->nz; A.ndx = g->ndx; A.ndz = g->ndz; A.n_proj = n_proj;
-    A.nzp = tomo_nzp(g->nz);
-    A.syp = A.nzp;
-    A.sxp = (g->ny + 2 * TOMO_PAD) * A.syp;
+    A.nzp = tomo_nzp(g->nz);                       // planes to visit; the pitches may be those of the next cube (tomo_pad_pitch)
+    int nyp;
+    tomo_pad_pitch(g->ny, g->nz, &nyp, &A.syp);
+    A.sxp = nyp * A.syp;
     tomo_grad_separable_tiles(g, &A.nxt, &A.nchunk);
     const double nblocks = sep_grid_blocks(A.nxt, A.nchunk, n_proj);
     if (nblocks >= 2147483647.0) { tomo_set_error("separable gradient: too many blocks for one launch"); return TOMO_E_RANGE; }

@@ -49,12 +49,34 @@ static_assert(V_END <= TOMO_VIEW_STRIDE, "view record overflows TOMO_VIEW_STRIDE
 #define TOMO_PAD_HEAD 32
 #define TOMO_PAD_TAIL 32
 
-// Row pitch (floats) of the padded volume along z.
+// Number of z planes of the padded volume the kernels address (zero border included, rounded up to 32).
 static inline
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 int tomo_nzp(int nz) { return ((nz + 2 * TOMO_PAD + 31) / 32) * 32; }
+
+// Pitches of the padded volume: *nyp rows per x plane, *syp floats per row (x stride = nyp * syp floats).  The natural pitches are
+// (ny + 2 TOMO_PAD, tomo_nzp(nz)).  The ray kernels have variants with compile-time strides for the pitches of the cubes
+// 64^3 ... 1024^3 (ray_core.h: all eight corner loads off one address register), so a volume whose (ny, nz) fits the next of those
+// cubes takes that cube's pitches when it costs at most twice the memory of the natural layout; the rows / planes beyond the
+// natural ones are never addressed.
+static inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+void tomo_pad_pitch(int ny, int nz, int* nyp, int* syp)
+{
+    const int ny0 = ny + 2 * TOMO_PAD, nz0 = tomo_nzp(nz);
+    *nyp = ny0; *syp = nz0;
+    for (int n = 64; n <= 1024; n *= 2) {
+        const int cy = n + 2 * TOMO_PAD, cz = tomo_nzp(n);
+        if (ny0 <= cy && nz0 <= cz) {
+            if ((double)cy * cz <= 2.0 * (double)ny0 * nz0) { *nyp = cy; *syp = cz; }
+            return;
+        }
+    }
+}
 
 // Tile of the scatter backprojector (back_kernels.cu); the host needs the xy extent to bound the
 // z drift of a ray inside a tile when it counts colour classes.
